@@ -1,0 +1,276 @@
+/* rgnn.h -- C ABI of librgnn_b200.so: B200 (sm_100a) kernels for RadarGNN's hot path.
+ *
+ * The reference (TUMFTM/RadarGNN) has no FFI of its own: its boundary for this path is
+ * a Python API backed by scikit-learn (KD-tree) and PyG / torch_scatter / cuBLAS.  The
+ * entry points below are what a binding for that path attaches to; each one names the
+ * reference interface it replaces (paths relative to the reference's
+ * src/gnnradarobjectdetection/).  radargnn_b200/_lib.py is the ctypes binding used by
+ * the Python mirror of the reference classes; INTEGRATION.md shows the stub a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types;
+ *   - pointers are DEVICE pointers unless the parameter name ends in `_host`;
+ *   - every function returns an rgnn_status (0 = ok), never throws, never allocates
+ *     device memory: scratch comes from the caller through `workspace`
+ *     (size from the matching *_workspace_bytes query; 256-byte aligned);
+ *   - all work is enqueued on `stream` (a cudaStream_t); functions that must hand a
+ *     count back to the host synchronise that stream and say so;
+ *   - matrices are dense row-major; edge_index is int64 [2, E] exactly as PyG wants it:
+ *     row 0 = the query point i (reference E[:,0]), row 1 = its neighbour j (E[:,1]).
+ */
+#ifndef RGNN_H_
+#define RGNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGNN_ABI_VERSION 1
+
+typedef void* rgnn_stream_t; /* cudaStream_t */
+
+typedef enum rgnn_status {
+  RGNN_OK = 0,
+  RGNN_ERR_INVALID_ARGUMENT = 1,
+  RGNN_ERR_K_NOT_SMALLER_THAN_N = 2, /* sklearn: ValueError "Expected n_neighbors < n_samples_fit" */
+  RGNN_ERR_WORKSPACE_TOO_SMALL = 3,
+  RGNN_ERR_CUDA = 4,
+  RGNN_ERR_DOT_PRODUCT = 5,     /* graph_constructor/features.py:56 "Error in dot product calculation" */
+  RGNN_ERR_INVALID_FEATURE = 6, /* graph_constructor/graph.py:220 "Invalid feature specified" */
+  RGNN_ERR_UNSUPPORTED = 7,
+  RGNN_ERR_NO_DEVICE = 8
+} rgnn_status;
+
+typedef enum rgnn_dtype { RGNN_F32 = 0, RGNN_F64 = 1 } rgnn_dtype;
+typedef enum rgnn_edge_mode { RGNN_DIRECTED = 0, RGNN_UNDIRECTED = 1 } rgnn_edge_mode;
+
+/* graph.py:139-223 feature names, in the order the caller lists them */
+typedef enum rgnn_edge_feature {
+  RGNN_EF_POINT_PAIR_FEATURES = 0,         /* 4 columns */
+  RGNN_EF_SPATIAL_EUCLIDEAN_DISTANCE = 1,  /* 1 */
+  RGNN_EF_VELOCITY_EUCLIDEAN_DISTANCE = 2, /* 1 */
+  RGNN_EF_RELATIVE_POSITION = 3,           /* 2 */
+  RGNN_EF_RELATIVE_VELOCITY = 4            /* 2 */
+} rgnn_edge_feature;
+
+/* graph.py:225-275 feature names */
+typedef enum rgnn_node_feature {
+  RGNN_NF_RCS = 0,
+  RGNN_NF_TIME_INDEX = 1,
+  RGNN_NF_DEGREE = 2,
+  RGNN_NF_VELOCITY_VECTOR_LENGTH = 3,
+  RGNN_NF_VELOCITY_VECTOR = 4,     /* 2 columns */
+  RGNN_NF_SPATIAL_COORDINATES = 5  /* 2 columns */
+} rgnn_node_feature;
+
+typedef enum rgnn_aggr { RGNN_AGGR_MAX = 0, RGNN_AGGR_ADD = 1, RGNN_AGGR_MEAN = 2, RGNN_AGGR_MIN = 3 } rgnn_aggr;
+typedef enum rgnn_conv_type { RGNN_CONV_MPNN = 0, RGNN_CONV_RADAR_POINT_GNN = 1 } rgnn_conv_type;
+
+#define RGNN_MAX_MLP_LAYERS 8
+#define RGNN_MAX_EDGE_FEATURES 8
+#define RGNN_MAX_NODE_FEATURES 8
+#define RGNN_MAX_K 64
+
+/* ------------------------------------------------------------------------------------ */
+/* library                                                                              */
+/* ------------------------------------------------------------------------------------ */
+int rgnn_abi_version(void);
+const char* rgnn_status_string(int status);
+/* Last CUDA error text seen by this thread ("" if none). */
+const char* rgnn_last_cuda_error(void);
+/* SM count / compute capability of the current device; RGNN_ERR_NO_DEVICE without a GPU. */
+int rgnn_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+int64_t rgnn_kernel_launch_count(void);
+
+/* Per-kernel device timing for bench.py's roofline line.  While enabled, every kernel family the
+ * library launches is bracketed by CUDA events on its launch stream.  collect() synchronises the
+ * recorded events, adds their durations to per-name totals and returns the number of names;
+ * entry(i) reads one total (name is owned by the library, valid until reset). */
+void rgnn_profile_enable(int32_t on);
+int32_t rgnn_profile_collect(void);
+int rgnn_profile_entry(int32_t index, const char** name, double* total_ms, int64_t* count);
+void rgnn_profile_reset(void);
+
+/* ------------------------------------------------------------------------------------ */
+/* neighbour search  (replaces Graph.build, graph_constructor/graph.py:32-82, i.e.       */
+/* sklearn kneighbors_graph / radius_neighbors_graph + nonzero())                        */
+/* ------------------------------------------------------------------------------------ */
+/* A batch of frames is one array of points plus frame_ptr_host[n_frames+1]; edges never
+ * cross frames (disjoint union, utils/data_handling.py:30); node ids are global.
+ * `basis` is the search space [n_points, dims] (dims = 2 for "X", 4 for "XV";
+ * preprocessor/radarscenes/dataset_creation.py:203-206), f32 or f64; distances are
+ * always evaluated in fp64 exactly as sklearn does (sum over dims of (a-b)*(a-b)). */
+size_t rgnn_graph_workspace_bytes(int64_t n_points, int32_t n_frames);
+
+/* Number of edges a k-NN build emits: sum over frames with n_f > 1 of n_f * k.
+ * Returns -1 and sets *status = RGNN_ERR_K_NOT_SMALLER_THAN_N if some frame has 1 < n_f <= k. */
+int64_t rgnn_knn_edge_count(const int64_t* frame_ptr_host, int32_t n_frames, int32_t k, int* status);
+
+/* k-NN graph (graph.py:52-66).  Row i*k..i*k+k-1 (per frame) lists the k nearest
+ * neighbours of point i by ascending (fp64 squared distance, index); self excluded by
+ * index; frames with n_f <= 1 emit nothing (graph.py:45). */
+int rgnn_graph_build_knn(const void* basis, int32_t basis_dtype, int32_t dims,
+                         const int64_t* frame_ptr_host, int32_t n_frames, int32_t k,
+                         int64_t* edge_index, int64_t n_edges,
+                         void* workspace, size_t workspace_bytes, rgnn_stream_t stream);
+
+/* Radius graph (graph.py:68-82), two calls sharing the workspace:
+ *   count: bins the points, counts  j != i with sum_d (a_d-b_d)^2 <= r*r  (fp64,
+ *          inclusive), synchronises `stream`, returns E in *n_edges_host;
+ *   fill:  writes edge_index [2, E]; rows ascend in i, columns ascend in j (canonical
+ *          order; sklearn's KD-tree order inside a row is not reproduced). */
+int rgnn_graph_build_radius_count(const void* basis, int32_t basis_dtype, int32_t dims,
+                                  const int64_t* frame_ptr_host, int32_t n_frames, double r,
+                                  int64_t* n_edges_host,
+                                  void* workspace, size_t workspace_bytes, rgnn_stream_t stream);
+int rgnn_graph_build_radius_fill(const void* basis, int32_t basis_dtype, int32_t dims,
+                                 const int64_t* frame_ptr_host, int32_t n_frames, double r,
+                                 int64_t* edge_index, int64_t n_edges,
+                                 void* workspace, size_t workspace_bytes, rgnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* edge / node features                                                                  */
+/* ------------------------------------------------------------------------------------ */
+/* Columns a feature list produces (graph.py:157-166); -1 for an unknown feature id. */
+int32_t rgnn_edge_feature_width(const int32_t* features_host, int32_t n_features);
+
+/* GeometricGraph.extract_node_pair_features (graph.py:139-223) +
+ * get_En_equivariant_point_pair_metrics (features.py:6-122): fp64 arithmetic per edge,
+ * written as `out_dtype` [E, De].  pos [N, pos_dims], vel [N, vel_dims] of `in_dtype`.
+ * *error_flag (device int32, zeroed by the call) becomes RGNN_ERR_DOT_PRODUCT if a
+ * normalised dot product exceeds 1 by 1e-3 or more (features.py:49-56). */
+int rgnn_edge_features(const void* pos, const void* vel, int32_t in_dtype,
+                       int32_t pos_dims, int32_t vel_dims, int64_t n_points,
+                       const int64_t* edge_index, int64_t n_edges,
+                       const int32_t* features_host, int32_t n_features, int32_t edge_mode,
+                       void* edge_attr, int32_t out_dtype, int32_t* error_flag,
+                       rgnn_stream_t stream);
+
+/* Graph.get_degree (graph.py:93-96): degree of the *undirected* graph networkx builds
+ * from the adjacency matrix, |N_out(i) U N_in(i)|.  edge_index rows must be grouped by
+ * ascending source (what the builders above emit). */
+int rgnn_undirected_degree(const int64_t* edge_index, int64_t n_edges, int64_t n_points,
+                           int32_t* degree, rgnn_stream_t stream);
+
+/* GeometricGraph.extract_single_node_features (graph.py:225-275): concatenates the
+ * listed columns into out [N, Fn] (`out_dtype`).  rcs / time_index [N] f64, degree [N]
+ * int32, pos / vel [N, 2] f64; unused inputs may be NULL. */
+int32_t rgnn_node_feature_width(const int32_t* features_host, int32_t n_features);
+int rgnn_node_features(const double* rcs, const double* time_index, const int32_t* degree,
+                       const double* pos, const double* vel, int64_t n_points,
+                       const int32_t* features_host, int32_t n_features,
+                       void* out, int32_t out_dtype, rgnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* message passing  (replaces PyG MessagePassing.propagate + torch_scatter + addmm under */
+/* MPNNConv / RadarPointGNNConv, gnn/mpnn_layers.py:86-101, 171-184)                     */
+/* ------------------------------------------------------------------------------------ */
+/* Target-major (CSC) view of edge_index: csc_ptr [N+1], and for every slot the source
+ * node (csc_src) and the position of that edge in edge_index / edge_attr (csc_eid).
+ * Messages are reduced at edge_index[1] (flow = source_to_target). */
+size_t rgnn_csc_workspace_bytes(int64_t n_nodes, int64_t n_edges);
+int rgnn_csc_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes,
+                   int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid,
+                   void* workspace, size_t workspace_bytes, rgnn_stream_t stream);
+
+/* One graph-convolution layer.  Weights are PyG `Linear` parameters: [out, in] row-major
+ * fp32, read at call time (the reference's tests swap them after construction).
+ *   MPNN:            m_e = pre_mlp([x_t ; x_s ; e'])     P = 2C + De  (3C with edge encoder)
+ *                    h_n = post_mlp([x_n ; aggr_e m_e])
+ *   RADAR_POINT_GNN: m_e = pre_mlp([x_s ; e])            P = C + De
+ *                    h_n = post_mlp([x_n ; aggr_e m_e]) + x_n
+ * pre_mlp  = Linear(P,P) [ReLU Linear(P,P)]*(pre_layers-1)
+ * post_mlp = Linear(P+C,C_out) [ReLU Linear(C_out,C_out)]*(post_layers-1)
+ * Nodes without incoming edge aggregate to 0 for every `aggr`. */
+typedef struct rgnn_conv_desc {
+  int32_t conv_type;   /* rgnn_conv_type */
+  int32_t aggr;        /* rgnn_aggr */
+  int32_t in_channels; /* C */
+  int32_t out_channels;
+  int32_t edge_dim;    /* De */
+  int32_t pre_layers;
+  int32_t post_layers;
+  int32_t use_edge_encoder;
+  const float* edge_encoder_weight; /* [C, De] or NULL */
+  const float* edge_encoder_bias;   /* [C] or NULL */
+  const float* pre_weight[RGNN_MAX_MLP_LAYERS];
+  const float* pre_bias[RGNN_MAX_MLP_LAYERS];
+  const float* post_weight[RGNN_MAX_MLP_LAYERS];
+  const float* post_bias[RGNN_MAX_MLP_LAYERS];
+} rgnn_conv_desc;
+
+size_t rgnn_conv_workspace_bytes(const rgnn_conv_desc* desc, int64_t n_nodes, int64_t n_edges);
+int rgnn_conv_forward(const rgnn_conv_desc* desc, const float* x, int64_t n_nodes,
+                      const int32_t* csc_ptr, const int32_t* csc_src, const int32_t* csc_eid,
+                      const float* edge_attr, int64_t n_edges, float* out,
+                      void* workspace, size_t workspace_bytes, rgnn_stream_t stream);
+
+/* PyG BatchNorm (= BatchNorm1d) in TRAINING mode followed by optional ReLU
+ * (gnn/gnn_models.py:126-128): batch statistics over all n rows, biased variance for
+ * the normalisation; running_mean / running_var (unbiased) updated with `momentum`
+ * when non-NULL.  weight / bias may be NULL (affine=False). */
+size_t rgnn_batchnorm_workspace_bytes(int64_t n, int32_t channels);
+int rgnn_batchnorm_relu_forward(const float* x, int64_t n, int32_t channels,
+                                const float* weight, const float* bias, float eps, float momentum,
+                                float* running_mean, float* running_var, int32_t apply_relu,
+                                float* out, void* workspace, size_t workspace_bytes,
+                                rgnn_stream_t stream);
+
+/* y[n, out] = act(x)[n, in] . W[out, in]^T + b  -- PyG `Linear` (embedding MLPs and heads,
+ * gnn/gnn_models.py:137-178).  relu_input applies ReLU to x on load. */
+int rgnn_linear_forward(const float* x, int64_t n, int32_t in_features, const float* weight,
+                        const float* bias, int32_t out_features, int32_t relu_input, float* y,
+                        rgnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* fused path: graph build + L-layer MPNN forward (the north-star hot path)               */
+/* ------------------------------------------------------------------------------------ */
+typedef struct rgnn_pipeline_desc {
+  int32_t search;  /* 0 = knn, 1 = radius (radius: n_edges must come from a prior count) */
+  int32_t k;
+  double r;
+  int32_t distance_dims;  /* 2 = "X", 4 = "XV" */
+  int32_t edge_mode;
+  int32_t n_edge_features;
+  int32_t edge_features[RGNN_MAX_EDGE_FEATURES];
+  int32_t n_layers;
+  const rgnn_conv_desc* layers;   /* HOST array [n_layers] */
+  const float* const* bn_weight;  /* HOST array of device pointers [n_layers], entries may be NULL */
+  const float* const* bn_bias;
+  float bn_eps;
+} rgnn_pipeline_desc;
+
+size_t rgnn_pipeline_workspace_bytes(const rgnn_pipeline_desc* desc, int64_t n_points,
+                                     int32_t n_frames, int64_t n_edges);
+
+/* Everything resident in HBM.  pos / vel f32 [N, 2]; x0 f32 [N, C0].  Outputs:
+ * edge_index int64 [2, E], edge_attr f32 [E, De], h f32 [N, C_last] with
+ * h = relu(bn(conv_L(... relu(bn(conv_1(x0)))))).  *error_flag as in rgnn_edge_features. */
+int rgnn_pipeline_forward(const rgnn_pipeline_desc* desc, const float* pos, const float* vel,
+                          const float* x0, const int64_t* frame_ptr_host, int32_t n_frames,
+                          int64_t* edge_index, int64_t n_edges, float* edge_attr, float* h,
+                          int32_t* error_flag, void* workspace, size_t workspace_bytes,
+                          rgnn_stream_t stream);
+
+/* Same path with HOST buffers (pinned or pageable): copies pos / vel / x0 to the device
+ * staging area inside `workspace`, runs the path, copies edge_index / edge_attr / h back
+ * and synchronises `stream`.  Output pointers may be NULL to skip that copy.
+ * workspace must hold rgnn_pipeline_host_workspace_bytes(). */
+size_t rgnn_pipeline_host_workspace_bytes(const rgnn_pipeline_desc* desc, int64_t n_points,
+                                          int32_t n_frames, int64_t n_edges, int32_t c0);
+int rgnn_pipeline_forward_host(const rgnn_pipeline_desc* desc, const float* pos_host,
+                               const float* vel_host, const float* x0_host, int32_t c0,
+                               const int64_t* frame_ptr_host, int32_t n_frames,
+                               int64_t* edge_index_host, int64_t n_edges, float* edge_attr_host,
+                               float* h_host, void* workspace, size_t workspace_bytes,
+                               rgnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGNN_H_ */

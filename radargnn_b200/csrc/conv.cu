@@ -1,0 +1,391 @@
+// conv.cu -- one graph-convolution layer: MPNNConv / RadarPointGNNConv forward
+// (reference gnn/mpnn_layers.py:86-101, 171-184; PyG propagate = index_select x2 -> cat ->
+// Linear -> torch_scatter reduce at edge_index[1] -> cat -> Linear).
+//
+// Factored formulation (hard part 4).  The first Linear of pre_mlp is
+// affine in its concatenated input, so with W_pre = [W_t | W_s | W_e] (column blocks for
+// x_i = x[target], x_j = x[source], edge attributes)
+//     m_e = W_t x_t + W_s x_s + W_e e_e + b
+// and two node-level contractions A = x W_t^T, B = x W_s^T replace the E x P x P per-edge GEMM:
+//     max:  M_n = A_n + b + max_e (B[s_e] + W_e e_e)           (0 when n has no incoming edge)
+//     add:  M_n = deg_n (A_n + b) + sum_e (B[s_e] + W_e e_e)
+//     mean: M_n = A_n + b + mean_e (B[s_e] + W_e e_e)          (0 when deg_n = 0)
+// The edge kernel is then a gather + segmented reduce over the CSC view, nothing is
+// materialised per edge.  With pre_layers > 1 (ReLU inside the message MLP) the per-edge
+// activations U = A[t] + B[s] + W_e e + b are materialised and pushed through the remaining
+// Linear layers before the segmented reduce.  An edge encoder (Linear De -> C) is folded into
+// W_e and b.  Results differ from the reference only by fp32 rounding order.
+#include <math.h>
+
+#include "conv.cuh"
+
+namespace rgnn {
+namespace {
+
+constexpr int kAggThreads = 256;
+
+// W_e (row-major [p, ldw], rows = output channels) -> shared [de][pp], zero padded
+__device__ __forceinline__ void stage_edge_weights(const float* __restrict__ w_e, int64_t ldw, int p, int pp,
+                                                   int de, float* __restrict__ smem) {
+  for (int i = threadIdx.x; i < de * pp; i += blockDim.x) {
+    const int d = i / pp, c = i - d * pp;
+    smem[i] = c < p ? w_e[static_cast<int64_t>(c) * ldw + d] : 0.f;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 fma4(float s, float4 w, float4 a) {
+  return make_float4(fmaf(s, w.x, a.x), fmaf(s, w.y, a.y), fmaf(s, w.z, a.z), fmaf(s, w.w, a.w));
+}
+__device__ __forceinline__ float4 max4(float4 a, float4 b) { return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w)); }
+__device__ __forceinline__ float4 min4(float4 a, float4 b) { return make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z), fminf(a.w, b.w)); }
+
+// One thread per (target node, 4-channel chunk).  MODE: rgnn_aggr, or -1 = write the per-edge
+// activations U[slot] = A[t] + B[s] + W_e e + b instead of reducing (general path).
+template <int MODE>
+__global__ void __launch_bounds__(kAggThreads)
+edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, int pp, int p,
+                      const float* __restrict__ bias, const float* __restrict__ w_e, int64_t ldwe, int de,
+                      const float* __restrict__ ea, const int32_t* __restrict__ csc_ptr,
+                      const int32_t* __restrict__ csc_src, int64_t n_nodes, float* __restrict__ out) {
+  extern __shared__ float w_s[];  // [de][pp]
+  stage_edge_weights(w_e, ldwe, p, pp, de, w_s);
+  const int chunks = pp >> 2;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t node = gid / chunks;
+  if (node >= n_nodes) return;
+  const int c0 = static_cast<int>(gid - node * chunks) << 2;
+  const int beg = csc_ptr[node], end = csc_ptr[node + 1];
+
+  float4 base = make_float4(0.f, 0.f, 0.f, 0.f);  // A_n + b for this chunk
+  if (a != nullptr) base = ld4(a + node * pp + c0);
+  {
+    float4 bb;
+    bb.x = c0 + 0 < p ? bias[c0 + 0] : 0.f;
+    bb.y = c0 + 1 < p ? bias[c0 + 1] : 0.f;
+    bb.z = c0 + 2 < p ? bias[c0 + 2] : 0.f;
+    bb.w = c0 + 3 < p ? bias[c0 + 3] : 0.f;
+    base = add4(base, bb);
+  }
+
+  float4 acc;
+  if (MODE == RGNN_AGGR_MAX) acc = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  else if (MODE == RGNN_AGGR_MIN) acc = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+  else acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto edge_term = [&](int slot, float4 v) {
+    const float* e = ea + static_cast<int64_t>(slot) * de;
+    for (int d = 0; d < de; ++d) v = fma4(e[d], ld4(w_s + d * pp + c0), v);
+    return v;
+  };
+
+  int slot = beg;
+  // 4 gathers in flight per thread
+  for (; slot + 4 <= end; slot += 4) {
+    const int s0 = csc_src[slot], s1 = csc_src[slot + 1], s2 = csc_src[slot + 2], s3 = csc_src[slot + 3];
+    float4 v0 = ld4(b + static_cast<int64_t>(s0) * pp + c0);
+    float4 v1 = ld4(b + static_cast<int64_t>(s1) * pp + c0);
+    float4 v2 = ld4(b + static_cast<int64_t>(s2) * pp + c0);
+    float4 v3 = ld4(b + static_cast<int64_t>(s3) * pp + c0);
+    v0 = edge_term(slot, v0); v1 = edge_term(slot + 1, v1);
+    v2 = edge_term(slot + 2, v2); v3 = edge_term(slot + 3, v3);
+    if (MODE == RGNN_AGGR_MAX) acc = max4(acc, max4(max4(v0, v1), max4(v2, v3)));
+    else if (MODE == RGNN_AGGR_MIN) acc = min4(acc, min4(min4(v0, v1), min4(v2, v3)));
+    else if (MODE == -1) {
+      *reinterpret_cast<float4*>(out + static_cast<int64_t>(slot) * pp + c0) = add4(base, v0);
+      *reinterpret_cast<float4*>(out + static_cast<int64_t>(slot + 1) * pp + c0) = add4(base, v1);
+      *reinterpret_cast<float4*>(out + static_cast<int64_t>(slot + 2) * pp + c0) = add4(base, v2);
+      *reinterpret_cast<float4*>(out + static_cast<int64_t>(slot + 3) * pp + c0) = add4(base, v3);
+    } else {  // add / mean: fixed slot order
+      acc = add4(acc, v0); acc = add4(acc, v1); acc = add4(acc, v2); acc = add4(acc, v3);
+    }
+  }
+  for (; slot < end; ++slot) {
+    float4 v = ld4(b + static_cast<int64_t>(csc_src[slot]) * pp + c0);
+    v = edge_term(slot, v);
+    if (MODE == RGNN_AGGR_MAX) acc = max4(acc, v);
+    else if (MODE == RGNN_AGGR_MIN) acc = min4(acc, v);
+    else if (MODE == -1) *reinterpret_cast<float4*>(out + static_cast<int64_t>(slot) * pp + c0) = add4(base, v);
+    else acc = add4(acc, v);
+  }
+  if (MODE == -1) return;
+  const int deg = end - beg;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);  // torch_scatter: empty segments aggregate to 0
+  if (deg > 0) {
+    if (MODE == RGNN_AGGR_MAX || MODE == RGNN_AGGR_MIN) r = add4(base, acc);
+    else if (MODE == RGNN_AGGR_ADD) {
+      const float fd = static_cast<float>(deg);
+      r = make_float4(fmaf(fd, base.x, acc.x), fmaf(fd, base.y, acc.y), fmaf(fd, base.z, acc.z), fmaf(fd, base.w, acc.w));
+    } else {
+      const float inv = 1.f / static_cast<float>(deg);
+      r = make_float4(fmaf(acc.x, inv, base.x), fmaf(acc.y, inv, base.y), fmaf(acc.z, inv, base.z), fmaf(acc.w, inv, base.w));
+    }
+  }
+  *reinterpret_cast<float4*>(out + node * pp + c0) = r;
+}
+
+// general path: M[n] = reduce over the node's slots of U[slot] (already through pre_mlp)
+template <int MODE>
+__global__ void __launch_bounds__(kAggThreads)
+segment_reduce_kernel(const float* __restrict__ u, int pp, const int32_t* __restrict__ csc_ptr, int64_t n_nodes,
+                      float* __restrict__ out) {
+  const int chunks = pp >> 2;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t node = gid / chunks;
+  if (node >= n_nodes) return;
+  const int c0 = static_cast<int>(gid - node * chunks) << 2;
+  const int beg = csc_ptr[node], end = csc_ptr[node + 1];
+  float4 acc;
+  if (MODE == RGNN_AGGR_MAX) acc = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  else if (MODE == RGNN_AGGR_MIN) acc = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+  else acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int slot = beg; slot < end; ++slot) {
+    const float4 v = ld4(u + static_cast<int64_t>(slot) * pp + c0);
+    if (MODE == RGNN_AGGR_MAX) acc = max4(acc, v);
+    else if (MODE == RGNN_AGGR_MIN) acc = min4(acc, v);
+    else acc = add4(acc, v);
+  }
+  const int deg = end - beg;
+  if (deg == 0) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  else if (MODE == RGNN_AGGR_MEAN) {
+    const float fd = static_cast<float>(deg);
+    acc = make_float4(acc.x / fd, acc.y / fd, acc.z / fd, acc.w / fd);
+  }
+  *reinterpret_cast<float4*>(out + node * pp + c0) = acc;
+}
+
+// w_eff[p, de] = W_pre[:, off:off+C] . W_enc[C, de];  b_eff[p] = b_pre + W_pre[:, off:off+C] . b_enc
+__global__ void fold_edge_encoder_kernel(const float* __restrict__ w_pre, int p, int off, int c,
+                                         const float* __restrict__ w_enc, const float* __restrict__ b_enc, int de,
+                                         const float* __restrict__ b_pre, float* __restrict__ w_eff,
+                                         float* __restrict__ b_eff) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p * (de + 1)) return;
+  const int row = idx / (de + 1), d = idx - row * (de + 1);
+  const float* wr = w_pre + static_cast<int64_t>(row) * p + off;
+  double acc = 0.0;
+  if (d < de) {
+    for (int j = 0; j < c; ++j) acc += static_cast<double>(wr[j]) * static_cast<double>(w_enc[j * de + d]);
+    w_eff[row * de + d] = static_cast<float>(acc);
+  } else {
+    for (int j = 0; j < c; ++j) acc += static_cast<double>(wr[j]) * static_cast<double>(b_enc[j]);
+    b_eff[row] = static_cast<float>(acc + static_cast<double>(b_pre[row]));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gather_edge_rows_kernel(const float* __restrict__ edge_attr, const int32_t* __restrict__ csc_eid, int64_t n_edges,
+                        int de, float* __restrict__ ea_csc) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n_edges * de) return;
+  const int64_t slot = idx / de;
+  const int d = static_cast<int>(idx - slot * de);
+  ea_csc[idx] = edge_attr[static_cast<int64_t>(csc_eid[slot]) * de + d];
+}
+
+template <int MODE>
+int launch_edge_aggregate(const float* a, const float* b, const ConvShape& s, const float* bias, const float* w_e,
+                          int64_t ldwe, const float* ea, const int32_t* csc_ptr, const int32_t* csc_src,
+                          int64_t n_nodes, float* out, cudaStream_t stream) {
+  const int64_t threads = n_nodes * (s.pp >> 2);
+  const size_t smem = sizeof(float) * s.de * s.pp;
+  RGNN_PROFILE("edge_aggregate", stream);
+  if (smem > 48 * 1024)
+    RGNN_CUDA_CHECK(cudaFuncSetAttribute(edge_aggregate_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+  edge_aggregate_kernel<MODE><<<div_up(threads, kAggThreads), kAggThreads, smem, stream>>>(
+      a, b, s.pp, s.p, bias, w_e, ldwe, s.de, ea, csc_ptr, csc_src, n_nodes, out);
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
+}
+
+}  // namespace
+
+int conv_shape(const rgnn_conv_desc& d, ConvShape* s) {
+  if (d.in_channels < 1 || d.out_channels < 1 || d.edge_dim < 0) return RGNN_ERR_INVALID_ARGUMENT;
+  if (d.pre_layers < 1 || d.pre_layers > RGNN_MAX_MLP_LAYERS || d.post_layers < 1 || d.post_layers > RGNN_MAX_MLP_LAYERS)
+    return RGNN_ERR_INVALID_ARGUMENT;
+  if (d.aggr < RGNN_AGGR_MAX || d.aggr > RGNN_AGGR_MIN) return RGNN_ERR_INVALID_ARGUMENT;
+  s->c = d.in_channels;
+  s->c_out = d.out_channels;
+  s->de = d.edge_dim;
+  if (d.conv_type == RGNN_CONV_MPNN) {
+    s->de_eff = d.use_edge_encoder ? d.in_channels : d.edge_dim;
+    s->p = 2 * d.in_channels + s->de_eff;
+  } else if (d.conv_type == RGNN_CONV_RADAR_POINT_GNN) {
+    if (d.use_edge_encoder) return RGNN_ERR_UNSUPPORTED;
+    if (d.out_channels != d.in_channels) return RGNN_ERR_INVALID_ARGUMENT;  // residual update
+    s->de_eff = d.edge_dim;
+    s->p = d.in_channels + d.edge_dim;
+  } else {
+    return RGNN_ERR_INVALID_ARGUMENT;
+  }
+  s->pp = (s->p + 3) & ~3;
+  s->general = d.pre_layers > 1;
+  for (int l = 0; l < d.pre_layers; ++l)
+    if (d.pre_weight[l] == nullptr || d.pre_bias[l] == nullptr) return RGNN_ERR_INVALID_ARGUMENT;
+  for (int l = 0; l < d.post_layers; ++l)
+    if (d.post_weight[l] == nullptr || d.post_bias[l] == nullptr) return RGNN_ERR_INVALID_ARGUMENT;
+  if (d.use_edge_encoder && (d.edge_encoder_weight == nullptr || d.edge_encoder_bias == nullptr))
+    return RGNN_ERR_INVALID_ARGUMENT;
+  return RGNN_OK;
+}
+
+int gather_edge_rows(const float* edge_attr, const int32_t* csc_eid, int64_t n_edges, int32_t de, float* ea_csc,
+                     cudaStream_t stream) {
+  if (n_edges == 0 || de == 0) return RGNN_OK;
+  RGNN_PROFILE("gather_edge_rows", stream);
+  gather_edge_rows_kernel<<<div_up(n_edges * de, 256), 256, 0, stream>>>(edge_attr, csc_eid, n_edges, de, ea_csc);
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
+}
+
+int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& in, int64_t n_nodes,
+                 const int32_t* csc_ptr, const int32_t* csc_src, const int32_t* csc_eid, const float* edge_attr,
+                 int64_t n_edges, float* out, const ConvWorkspace& w, cudaStream_t stream) {
+  if (n_nodes == 0) return RGNN_OK;
+  const bool mpnn = d.conv_type == RGNN_CONV_MPNN;
+  const int x_s_off = mpnn ? s.c : 0;            // column block of x_j in W_pre
+  const int e_off = mpnn ? 2 * s.c : s.c;        // column block of the edge attributes
+
+  // edge attributes in CSC slot order
+  const float* ea = edge_attr;
+  if (csc_eid != nullptr && s.de > 0) {
+    RGNN_RETURN_IF_ERROR(gather_edge_rows(edge_attr, csc_eid, n_edges, s.de, w.ea_csc, stream));
+    ea = w.ea_csc;
+  }
+
+  // edge-term weights: W_e [p, de] with row stride ldwe, bias b [p]
+  const float* w_e = d.pre_weight[0] + e_off;
+  int64_t ldwe = s.p;
+  const float* bias = d.pre_bias[0];
+  if (d.use_edge_encoder) {
+    fold_edge_encoder_kernel<<<div_up(s.p * (s.de + 1), 128), 128, 0, stream>>>(
+        d.pre_weight[0], s.p, e_off, s.c, d.edge_encoder_weight, d.edge_encoder_bias, s.de, d.pre_bias[0],
+        w.w_eff, w.b_eff);
+    RGNN_LAUNCH_CHECK();
+    w_e = w.w_eff; ldwe = s.de; bias = w.b_eff;
+  }
+
+  // node-level halves of the first message Linear
+  LinearArgs la;
+  la.a1 = in.x; la.lda1 = in.ldx; la.k1 = s.c;
+  la.a1_mean = in.mean; la.a1_scale = in.scale; la.a1_beta = in.beta; la.relu_a1 = in.relu;
+  la.ldw = s.p; la.m = n_nodes; la.n = s.p; la.ldy = s.pp;
+  la.tag = "linear_pre_node";
+  if (mpnn) {
+    la.w = d.pre_weight[0]; la.y = w.a;
+    RGNN_RETURN_IF_ERROR(launch_linear(la, stream));
+  }
+  la.w = d.pre_weight[0] + x_s_off; la.y = w.b;
+  RGNN_RETURN_IF_ERROR(launch_linear(la, stream));
+
+  const float* a_term = mpnn ? w.a : nullptr;
+  if (!s.general) {
+    switch (d.aggr) {
+      case RGNN_AGGR_MAX: RGNN_RETURN_IF_ERROR(launch_edge_aggregate<RGNN_AGGR_MAX>(a_term, w.b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, w.m, stream)); break;
+      case RGNN_AGGR_MIN: RGNN_RETURN_IF_ERROR(launch_edge_aggregate<RGNN_AGGR_MIN>(a_term, w.b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, w.m, stream)); break;
+      case RGNN_AGGR_ADD: RGNN_RETURN_IF_ERROR(launch_edge_aggregate<RGNN_AGGR_ADD>(a_term, w.b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, w.m, stream)); break;
+      default: RGNN_RETURN_IF_ERROR(launch_edge_aggregate<RGNN_AGGR_MEAN>(a_term, w.b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, w.m, stream)); break;
+    }
+  } else {
+    // per-edge activations through the remaining Linear layers, then the segmented reduce
+    RGNN_RETURN_IF_ERROR(launch_edge_aggregate<-1>(a_term, w.b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, w.u1, stream));
+    float* cur = w.u1;
+    float* nxt = w.u2;
+    for (int l = 1; l < d.pre_layers; ++l) {
+      LinearArgs lu;
+      lu.a1 = cur; lu.lda1 = s.pp; lu.k1 = s.p; lu.relu_a1 = 1;
+      lu.w = d.pre_weight[l]; lu.ldw = s.p; lu.bias = d.pre_bias[l];
+      lu.y = nxt; lu.ldy = s.pp; lu.m = n_edges; lu.n = s.p;
+      lu.tag = "linear_pre_edge";
+      RGNN_RETURN_IF_ERROR(launch_linear(lu, stream));
+      float* t = cur; cur = nxt; nxt = t;
+    }
+    const int64_t threads = n_nodes * (s.pp >> 2);
+    const unsigned blocks = div_up(threads, kAggThreads);
+    switch (d.aggr) {
+      case RGNN_AGGR_MAX: segment_reduce_kernel<RGNN_AGGR_MAX><<<blocks, kAggThreads, 0, stream>>>(cur, s.pp, csc_ptr, n_nodes, w.m); break;
+      case RGNN_AGGR_MIN: segment_reduce_kernel<RGNN_AGGR_MIN><<<blocks, kAggThreads, 0, stream>>>(cur, s.pp, csc_ptr, n_nodes, w.m); break;
+      case RGNN_AGGR_ADD: segment_reduce_kernel<RGNN_AGGR_ADD><<<blocks, kAggThreads, 0, stream>>>(cur, s.pp, csc_ptr, n_nodes, w.m); break;
+      default: segment_reduce_kernel<RGNN_AGGR_MEAN><<<blocks, kAggThreads, 0, stream>>>(cur, s.pp, csc_ptr, n_nodes, w.m); break;
+    }
+    RGNN_LAUNCH_CHECK();
+  }
+
+  // node update: post_mlp([x ; M]) (+ x for RadarPointGNNConv)
+  float* cur_out = d.post_layers == 1 ? out : w.t1;
+  LinearArgs lp;
+  lp.a1 = in.x; lp.lda1 = in.ldx; lp.k1 = s.c;
+  lp.a1_mean = in.mean; lp.a1_scale = in.scale; lp.a1_beta = in.beta; lp.relu_a1 = in.relu;
+  lp.a2 = w.m; lp.lda2 = s.pp; lp.k2 = s.p;
+  lp.w = d.post_weight[0]; lp.ldw = s.c + s.p; lp.bias = d.post_bias[0];
+  lp.y = cur_out; lp.ldy = s.c_out; lp.m = n_nodes; lp.n = s.c_out;
+  lp.tag = "linear_post";
+  if (!mpnn && d.post_layers == 1) {
+    lp.residual = in.x; lp.ldr = in.ldx;
+    lp.res_mean = in.mean; lp.res_scale = in.scale; lp.res_beta = in.beta; lp.res_relu = in.relu;
+  }
+  RGNN_RETURN_IF_ERROR(launch_linear(lp, stream));
+  for (int l = 1; l < d.post_layers; ++l) {
+    const bool last = l == d.post_layers - 1;
+    float* nxt = last ? out : (cur_out == w.t1 ? w.t2 : w.t1);
+    LinearArgs lq;
+    lq.a1 = cur_out; lq.lda1 = s.c_out; lq.k1 = s.c_out; lq.relu_a1 = 1;
+    lq.w = d.post_weight[l]; lq.ldw = s.c_out; lq.bias = d.post_bias[l];
+    lq.y = nxt; lq.ldy = s.c_out; lq.m = n_nodes; lq.n = s.c_out;
+    if (!mpnn && last) {
+      // residual is the (normalised) layer input, not the intermediate activation
+      lq.residual = in.x; lq.ldr = in.ldx;
+      lq.res_mean = in.mean; lq.res_scale = in.scale; lq.res_beta = in.beta; lq.res_relu = in.relu;
+    }
+    RGNN_RETURN_IF_ERROR(launch_linear(lq, stream));
+    cur_out = nxt;
+  }
+  return RGNN_OK;
+}
+
+}  // namespace rgnn
+
+using namespace rgnn;
+
+extern "C" {
+
+size_t rgnn_conv_workspace_bytes(const rgnn_conv_desc* desc, int64_t n_nodes, int64_t n_edges) {
+  ConvShape s;
+  if (desc == nullptr || n_nodes < 0 || n_edges < 0) return 0;
+  // sizing only needs the dimensions: tolerate null weight pointers here
+  rgnn_conv_desc d = *desc;
+  static const float dummy = 0.f;
+  for (int l = 0; l < RGNN_MAX_MLP_LAYERS; ++l) {
+    d.pre_weight[l] = d.pre_bias[l] = d.post_weight[l] = d.post_bias[l] = &dummy;
+  }
+  d.edge_encoder_weight = d.edge_encoder_bias = &dummy;
+  if (conv_shape(d, &s) != RGNN_OK) return 0;
+  SizeArena a;
+  carve_conv_workspace(a, d, s, n_nodes, n_edges, true);
+  return a.used;
+}
+
+int rgnn_conv_forward(const rgnn_conv_desc* desc, const float* x, int64_t n_nodes, const int32_t* csc_ptr,
+                      const int32_t* csc_src, const int32_t* csc_eid, const float* edge_attr, int64_t n_edges,
+                      float* out, void* workspace, size_t workspace_bytes, rgnn_stream_t stream) {
+  if (desc == nullptr || n_nodes < 0 || n_edges < 0) return RGNN_ERR_INVALID_ARGUMENT;
+  ConvShape s;
+  RGNN_RETURN_IF_ERROR(conv_shape(*desc, &s));
+  if (n_nodes == 0) return RGNN_OK;
+  if (x == nullptr || out == nullptr || csc_ptr == nullptr) return RGNN_ERR_INVALID_ARGUMENT;
+  if (n_edges > 0 && (csc_src == nullptr || (s.de > 0 && edge_attr == nullptr))) return RGNN_ERR_INVALID_ARGUMENT;
+  if (workspace == nullptr || workspace_bytes < rgnn_conv_workspace_bytes(desc, n_nodes, n_edges)) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  Arena arena(workspace, workspace_bytes);
+  ConvWorkspace w = carve_conv_workspace(arena, *desc, s, n_nodes, n_edges, true);
+  if (arena.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  ConvInput in;
+  in.x = x; in.ldx = s.c;
+  return conv_forward(*desc, s, in, n_nodes, csc_ptr, csc_src, csc_eid, edge_attr, n_edges, out, w,
+                      static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// csc.cu -- target-major (CSC) view of edge_index for the scatter-aggregate.
+// PyG's MessagePassing (flow = source_to_target) reduces the messages at edge_index[1]
+// (reference gnn/mpnn_layers.py:88,173 through propagate / torch_scatter).  Grouping the edges
+// by target once turns that atomic scatter into a segmented reduction: csc_ptr [N+1],
+// csc_src [E] (source node of every slot) and csc_eid [E] (edge id, ascending inside a
+// segment, so that sum / mean aggregate in a fixed order and are run-to-run deterministic).
+#include "csc.cuh"
+
+namespace rgnn {
+namespace {
+
+__global__ void __launch_bounds__(256)
+count_targets_kernel(const int64_t* __restrict__ dst, int64_t n_edges, int32_t* __restrict__ count) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e < n_edges) atomicAdd(&count[dst[e]], 1);
+}
+
+__global__ void __launch_bounds__(256)
+fill_slots_kernel(const int64_t* __restrict__ edge_index, int64_t n_edges, const int32_t* __restrict__ csc_ptr,
+                  int32_t* __restrict__ cursor, int32_t* __restrict__ csc_src, int32_t* __restrict__ csc_eid) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int64_t t = edge_index[n_edges + e];
+  const int pos = csc_ptr[t] + atomicAdd(&cursor[t], 1);
+  csc_eid[pos] = static_cast<int32_t>(e);
+  csc_src[pos] = static_cast<int32_t>(edge_index[e]);
+}
+
+// one thread per target: order the segment by edge id (segments are short: in-degree)
+__global__ void __launch_bounds__(128)
+sort_segments_kernel(const int32_t* __restrict__ csc_ptr, int64_t n_nodes, int32_t* __restrict__ csc_src,
+                     int32_t* __restrict__ csc_eid) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n_nodes) return;
+  const int b = csc_ptr[t], n = csc_ptr[t + 1] - b;
+  int32_t* eid = csc_eid + b;
+  int32_t* src = csc_src + b;
+  if (n < 2) return;
+  if (n <= 32) {
+    for (int j = 1; j < n; ++j) {
+      const int32_t ke = eid[j], ks = src[j];
+      int m = j - 1;
+      while (m >= 0 && eid[m] > ke) { eid[m + 1] = eid[m]; src[m + 1] = src[m]; --m; }
+      eid[m + 1] = ke; src[m + 1] = ks;
+    }
+    return;
+  }
+  auto swap = [&](int a, int c) {
+    const int32_t te = eid[a], ts = src[a];
+    eid[a] = eid[c]; src[a] = src[c]; eid[c] = te; src[c] = ts;
+  };
+  auto sift = [&](int start, int end) {
+    int root = start;
+    while (2 * root + 1 <= end) {
+      int child = 2 * root + 1;
+      if (child + 1 <= end && eid[child] < eid[child + 1]) ++child;
+      if (eid[root] < eid[child]) { swap(root, child); root = child; } else return;
+    }
+  };
+  for (int s = (n - 2) / 2; s >= 0; --s) sift(s, n - 1);
+  for (int end = n - 1; end > 0; --end) { swap(0, end); sift(0, end - 1); }
+}
+
+}  // namespace
+
+int csc_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, bool counts_ready,
+              bool ordered, const CscWorkspace& w, int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid,
+              cudaStream_t stream) {
+  RGNN_PROFILE("csc_build", stream);
+  if (!counts_ready) {
+    RGNN_CUDA_CHECK(cudaMemsetAsync(w.count, 0, sizeof(int32_t) * (n_nodes + 1), stream));
+    if (n_edges > 0) {
+      count_targets_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index + n_edges, n_edges, w.count);
+      RGNN_LAUNCH_CHECK();
+    }
+  }
+  RGNN_RETURN_IF_ERROR(exclusive_scan_i32(w.count, csc_ptr, n_nodes, w.scan_scratch, stream));
+  if (n_edges == 0) return RGNN_OK;
+  RGNN_CUDA_CHECK(cudaMemsetAsync(w.cursor, 0, sizeof(int32_t) * (n_nodes + 1), stream));
+  fill_slots_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index, n_edges, csc_ptr, w.cursor, csc_src, csc_eid);
+  RGNN_LAUNCH_CHECK();
+  if (ordered) {
+    sort_segments_kernel<<<div_up(n_nodes, 128), 128, 0, stream>>>(csc_ptr, n_nodes, csc_src, csc_eid);
+    RGNN_LAUNCH_CHECK();
+  }
+  return RGNN_OK;
+}
+
+}  // namespace rgnn
+
+using namespace rgnn;
+
+extern "C" {
+
+size_t rgnn_csc_workspace_bytes(int64_t n_nodes, int64_t n_edges) {
+  (void)n_edges;
+  if (n_nodes < 0) return 0;
+  SizeArena a;
+  carve_csc_workspace(a, n_nodes);
+  return a.used;
+}
+
+int rgnn_csc_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int32_t* csc_ptr,
+                   int32_t* csc_src, int32_t* csc_eid, void* workspace, size_t workspace_bytes,
+                   rgnn_stream_t stream) {
+  if (n_nodes < 0 || n_edges < 0 || n_edges > 0x7ffffff0LL || n_nodes > 0x7ffffff0LL) return RGNN_ERR_INVALID_ARGUMENT;
+  if (csc_ptr == nullptr || (n_edges > 0 && (edge_index == nullptr || csc_src == nullptr || csc_eid == nullptr)))
+    return RGNN_ERR_INVALID_ARGUMENT;
+  if (workspace == nullptr || workspace_bytes < rgnn_csc_workspace_bytes(n_nodes, n_edges)) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  Arena arena(workspace, workspace_bytes);
+  CscWorkspace w = carve_csc_workspace(arena, n_nodes);
+  if (arena.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  return csc_build(edge_index, n_edges, n_nodes, false, true, w, csc_ptr, csc_src, csc_eid,
+                   static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,621 @@
+// graph_build.cu -- neighbour search on the GPU: uniform cell lists + exact k-NN / radius
+// queries.  Replaces Graph.build (reference graph_constructor/graph.py:32-82), i.e.
+// sklearn's KD-tree behind kneighbors_graph / radius_neighbors_graph.
+//
+// Exactness contract (hard parts 1-2): distances are the fp64 reduced
+// distances sklearn computes -- sum over the dimensions, left to right, of (a - b) * (a - b)
+// with no fused multiply-add -- so membership (radius: d2 <= r*r, inclusive) and order
+// (k-NN: ascending (d2, index)) are bit-identical to the CPU oracle.  The cell list only
+// prunes: a ring search stops when the k-th best distance is strictly inside the distance to
+// the unsearched region (with a safety slack against cell-assignment rounding).
+#include <math.h>
+
+#include <vector>
+
+#include "graph_build.cuh"
+
+namespace rgnn {
+
+int64_t graph_total_cells_bound(int64_t n_points, int32_t n_frames) {
+  return 2 * (n_points / kPointsPerCell) + 6 * static_cast<int64_t>(n_frames) + 8;
+}
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ int find_frame(const int64_t* __restrict__ frame_ptr, int n_frames, int64_t i) {
+  int lo = 0, hi = n_frames;  // frame f holds [ptr[f], ptr[f+1])
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (frame_ptr[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+frame_bbox_kernel(const T* __restrict__ basis, int dims, int64_t n, const int64_t* __restrict__ frame_ptr,
+                  int n_frames, long long* __restrict__ bbox) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  int f = -1;
+  double x = 0.0, y = 0.0;
+  if (valid) {
+    f = n_frames == 1 ? 0 : find_frame(frame_ptr, n_frames, i);
+    x = static_cast<double>(basis[i * dims]);
+    y = static_cast<double>(basis[i * dims + 1]);
+  }
+  const unsigned full = 0xffffffffu;
+  const int f0 = __shfl_sync(full, f, 0);
+  const bool uniform = __all_sync(full, f == f0) && f0 >= 0;
+  if (uniform) {
+    double mnx = x, mny = y, mxx = x, mxy = y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mnx = fmin(mnx, __shfl_xor_sync(full, mnx, o));
+      mny = fmin(mny, __shfl_xor_sync(full, mny, o));
+      mxx = fmax(mxx, __shfl_xor_sync(full, mxx, o));
+      mxy = fmax(mxy, __shfl_xor_sync(full, mxy, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&bbox[f0 * 4 + 0], double_to_ordered(mnx));
+      atomicMin(&bbox[f0 * 4 + 1], double_to_ordered(mny));
+      atomicMax(&bbox[f0 * 4 + 2], double_to_ordered(mxx));
+      atomicMax(&bbox[f0 * 4 + 3], double_to_ordered(mxy));
+    }
+  } else if (valid) {
+    atomicMin(&bbox[f * 4 + 0], double_to_ordered(x));
+    atomicMin(&bbox[f * 4 + 1], double_to_ordered(y));
+    atomicMax(&bbox[f * 4 + 2], double_to_ordered(x));
+    atomicMax(&bbox[f * 4 + 3], double_to_ordered(y));
+  }
+}
+
+__global__ void init_bbox_kernel(long long* bbox, int n_frames) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_frames * 4) bbox[i] = (i & 3) < 2 ? 0x7fffffffffffffffLL : (long long)0x8000000000000000ULL;
+}
+
+// One thread per frame: choose the cell size so that a cell holds ~kPointsPerCell points.
+__global__ void frame_grid_kernel(const long long* __restrict__ bbox, const int64_t* __restrict__ frame_ptr,
+                                  const int64_t* __restrict__ frame_edge_off,
+                                  const int32_t* __restrict__ frame_cell_off, int n_frames,
+                                  FrameGrid* __restrict__ grids) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  FrameGrid g;
+  g.pt_begin = frame_ptr[f];
+  g.pt_end = frame_ptr[f + 1];
+  g.edge_off = frame_edge_off[f];
+  g.cell_off = frame_cell_off[f];
+  const int64_t nf = g.pt_end - g.pt_begin;
+  g.active = nf > 1 ? 1 : 0;
+  const int cap = frame_cell_off[f + 1] - frame_cell_off[f];
+  if (nf <= 0) {
+    g.x0 = g.y0 = 0.0; g.h = 1.0; g.inv_h = 1.0; g.gx = g.gy = 1;
+    grids[f] = g;
+    return;
+  }
+  const double mnx = ordered_to_double(bbox[f * 4 + 0]), mny = ordered_to_double(bbox[f * 4 + 1]);
+  const double mxx = ordered_to_double(bbox[f * 4 + 2]), mxy = ordered_to_double(bbox[f * 4 + 3]);
+  const double w = mxx - mnx, hgt = mxy - mny;
+  double target = static_cast<double>(nf) / kPointsPerCell;
+  if (target < 1.0) target = 1.0;
+  double h;
+  if (!(w > 0.0) && !(hgt > 0.0)) h = 1.0;
+  else if (!(hgt > 0.0)) h = w / target;
+  else if (!(w > 0.0)) h = hgt / target;
+  else h = sqrt(w * hgt / target);
+  if (!(h > 0.0) || !isfinite(h)) h = 1.0;
+  int gx, gy;
+  for (int it = 0; it < 200; ++it) {
+    const double fx = floor(w / h) + 1.0, fy = floor(hgt / h) + 1.0;
+    if (fx * fy <= static_cast<double>(cap)) { gx = static_cast<int>(fx); gy = static_cast<int>(fy); break; }
+    h *= 1.25;
+    gx = gy = 1;
+  }
+  if (static_cast<int64_t>(gx) * gy > cap) { gx = gy = 1; h = fmax(w, hgt) * 2.0 + 1.0; }
+  g.x0 = mnx; g.y0 = mny; g.h = h; g.inv_h = 1.0 / h; g.gx = gx; g.gy = gy;
+  grids[f] = g;
+}
+
+__device__ __forceinline__ int cell_coord(double v, double origin, double inv_h, int n) {
+  int c = static_cast<int>(floor((v - origin) * inv_h));
+  return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bin_count_kernel(const T* __restrict__ basis, int dims, int64_t n, const int64_t* __restrict__ frame_ptr,
+                 int n_frames, const FrameGrid* __restrict__ grids, int32_t* __restrict__ point_cell,
+                 int32_t* __restrict__ cell_count) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int f = n_frames == 1 ? 0 : find_frame(frame_ptr, n_frames, i);
+  const FrameGrid g = grids[f];
+  const double x = static_cast<double>(basis[i * dims]), y = static_cast<double>(basis[i * dims + 1]);
+  const int cx = cell_coord(x, g.x0, g.inv_h, g.gx), cy = cell_coord(y, g.y0, g.inv_h, g.gy);
+  const int cell = g.cell_off + cy * g.gx + cx;
+  point_cell[i] = cell;
+  atomicAdd(&cell_count[cell], 1);
+}
+
+template <typename T, int DIMS>
+__global__ void __launch_bounds__(kThreads)
+bin_scatter_kernel(const T* __restrict__ basis, int64_t n, const int64_t* __restrict__ frame_ptr, int n_frames,
+                   const int32_t* __restrict__ point_cell, const int32_t* __restrict__ cell_start,
+                   int32_t* __restrict__ cell_cursor, int32_t* __restrict__ sorted_idx,
+                   int32_t* __restrict__ sorted_cell, int32_t* __restrict__ sorted_frame,
+                   T* __restrict__ sorted_pts) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int cell = point_cell[i];
+  const int pos = cell_start[cell] + atomicAdd(&cell_cursor[cell], 1);
+  sorted_idx[pos] = static_cast<int32_t>(i);
+  sorted_cell[pos] = cell;
+  sorted_frame[pos] = n_frames == 1 ? 0 : find_frame(frame_ptr, n_frames, i);
+#pragma unroll
+  for (int d = 0; d < DIMS; ++d) sorted_pts[static_cast<int64_t>(pos) * DIMS + d] = basis[i * DIMS + d];
+}
+
+// ---- exact reduced distance ---------------------------------------------------------
+template <typename T, int DIMS>
+struct Point {
+  double v[DIMS];
+  __device__ __forceinline__ void load(const T* __restrict__ p) {
+    if constexpr (sizeof(T) == 4 && DIMS == 2) {
+      const float2 t = *reinterpret_cast<const float2*>(p);
+      v[0] = t.x; v[1] = t.y;
+    } else if constexpr (sizeof(T) == 4 && DIMS == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(p);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if constexpr (sizeof(T) == 8 && DIMS == 2) {
+      const double2 t = *reinterpret_cast<const double2*>(p);
+      v[0] = t.x; v[1] = t.y;
+    } else {
+#pragma unroll
+      for (int d = 0; d < DIMS; ++d) v[d] = static_cast<double>(p[d]);
+    }
+  }
+};
+
+template <int DIMS>
+__device__ __forceinline__ double rdist(const double* a, const double* b) {
+  // sklearn euclidean_rdist: d = 0; for j: tmp = a[j] - b[j]; d += tmp * tmp   (no FMA)
+  double acc = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIMS; ++d) {
+    const double t = __dsub_rn(a[d], b[d]);
+    acc = __dadd_rn(acc, __dmul_rn(t, t));
+  }
+  return acc;
+}
+
+__device__ __forceinline__ bool cand_less(double d, int id, double wd, int wid) {
+  return d < wd || (d == wd && id < wid);
+}
+
+// ---- k-NN query: one thread per point, in cell-sorted order ------------------------------
+template <typename T, int DIMS, int KMAX>
+__global__ void __launch_bounds__(128)
+knn_query_kernel(const T* __restrict__ sorted_pts, const int32_t* __restrict__ sorted_idx,
+                 const int32_t* __restrict__ sorted_cell, const int32_t* __restrict__ sorted_frame,
+                 const int32_t* __restrict__ cell_start, const FrameGrid* __restrict__ grids,
+                 int64_t n_points, int k, int64_t* __restrict__ edge_index, int64_t n_edges,
+                 int32_t* __restrict__ in_degree) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= n_points) return;
+  const FrameGrid g = grids[sorted_frame[q]];
+  if (!g.active) return;
+  Point<T, DIMS> me;
+  me.load(sorted_pts + q * DIMS);
+  const int c = sorted_cell[q] - g.cell_off;
+  const int cy = c / g.gx, cx = c - cy * g.gx;
+
+  // best-k list kept in DESCENDING order: slot 0 is always the current k-th (worst) entry, so
+  // the pruning bound needs no dynamic register index.  Slots >= k hold a -inf sentinel that
+  // no candidate can pass.
+  double bd[KMAX];
+  int bi[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    bd[j] = j < k ? INFINITY : -INFINITY;
+    bi[j] = j < k ? 0x7fffffff : -1;
+  }
+
+  const double slack = 1e-7 * g.h + 1e-14 * (fabs(me.v[0]) + fabs(me.v[1]) + fabs(g.x0) + fabs(g.y0));
+  const int max_ring = g.gx > g.gy ? g.gx : g.gy;
+  for (int r = 0; r <= max_ring; ++r) {
+    const int x0 = cx - r, x1 = cx + r, y0 = cy - r, y1 = cy + r;
+    // ring r = top row, bottom row, then the left / right cell of every row in between:
+    // one loop over the 4r spans so that the scan body exists once (keeps bd / bi in registers)
+    const int n_spans = r == 0 ? 1 : 4 * r;
+    for (int s = 0; s < n_spans; ++s) {
+      int row, xa, xb;
+      if (s < 2) {
+        row = s == 0 ? y0 : y1;
+        xa = x0 < 0 ? 0 : x0;
+        xb = x1 >= g.gx ? g.gx - 1 : x1;
+        if (r == 0) { xa = cx; xb = cx; }
+      } else {
+        row = y0 + 1 + ((s - 2) >> 1);
+        xa = xb = ((s - 2) & 1) ? x1 : x0;
+        if (xa < 0 || xa >= g.gx) continue;
+      }
+      if (row < 0 || row >= g.gy) continue;
+      const int base = g.cell_off + row * g.gx;
+      const int p0 = cell_start[base + xa], p1 = cell_start[base + xb + 1];
+      for (int p = p0; p < p1; ++p) {
+        if (p == q) continue;  // self is excluded by index, never by distance
+        Point<T, DIMS> o;
+        o.load(sorted_pts + static_cast<int64_t>(p) * DIMS);
+        const double d = rdist<DIMS>(me.v, o.v);
+        if (d <= bd[0]) {
+          const int id = sorted_idx[p];
+          if (cand_less(d, id, bd[0], bi[0])) {
+            bool prev = true;  // candidate beats slot j
+#pragma unroll
+            for (int j = 0; j < KMAX - 1; ++j) {
+              const bool sh = cand_less(d, id, bd[j + 1], bi[j + 1]);  // slot j+1 moves down to j
+              bd[j] = sh ? bd[j + 1] : (prev ? d : bd[j]);
+              bi[j] = sh ? bi[j + 1] : (prev ? id : bi[j]);
+              prev = sh;
+            }
+            if (prev) { bd[KMAX - 1] = d; bi[KMAX - 1] = id; }
+          }
+        }
+      }
+    }
+    // distance from the query to the nearest unsearched region (nothing lies beyond the grid)
+    double gap = INFINITY;
+    if (x0 > 0) gap = fmin(gap, me.v[0] - (g.x0 + x0 * g.h));
+    if (x1 < g.gx - 1) gap = fmin(gap, (g.x0 + (x1 + 1) * g.h) - me.v[0]);
+    if (y0 > 0) gap = fmin(gap, me.v[1] - (g.y0 + y0 * g.h));
+    if (y1 < g.gy - 1) gap = fmin(gap, (g.y0 + (y1 + 1) * g.h) - me.v[1]);
+    if (gap == INFINITY) break;  // whole frame searched
+    gap -= slack;
+    if (gap > 0.0 && bd[0] < gap * gap) break;
+  }
+
+  const int i = sorted_idx[q];
+  const int64_t e0 = g.edge_off + (static_cast<int64_t>(i) - g.pt_begin) * k;
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    if (j < k) {  // slot j is the (k-1-j)-th nearest
+      edge_index[e0 + (k - 1 - j)] = i;
+      edge_index[n_edges + e0 + (k - 1 - j)] = bi[j];
+      if (in_degree != nullptr) atomicAdd(&in_degree[bi[j]], 1);
+    }
+  }
+}
+
+// ---- radius query: count, then fill (rows ascending in j after sort_rows_kernel) -------------
+template <typename T, int DIMS, bool FILL>
+__global__ void __launch_bounds__(128)
+radius_query_kernel(const T* __restrict__ sorted_pts, const int32_t* __restrict__ sorted_idx,
+                    const int32_t* __restrict__ sorted_cell, const int32_t* __restrict__ sorted_frame,
+                    const int32_t* __restrict__ cell_start, const FrameGrid* __restrict__ grids,
+                    int64_t n_points, double r, double r2, int32_t* __restrict__ row_count,
+                    const int64_t* __restrict__ row_ptr, int64_t* __restrict__ edge_index, int64_t n_edges) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= n_points) return;
+  const int i = sorted_idx[q];
+  const FrameGrid g = grids[sorted_frame[q]];
+  if (!g.active) { if (!FILL) row_count[i] = 0; return; }
+  Point<T, DIMS> me;
+  me.load(sorted_pts + q * DIMS);
+  const double slack = 1e-7 * g.h + 1e-14 * (fabs(me.v[0]) + fabs(me.v[1]) + fabs(g.x0) + fabs(g.y0));
+  const double reach = r + slack;
+  const int xa = cell_coord(me.v[0] - reach, g.x0, g.inv_h, g.gx), xb = cell_coord(me.v[0] + reach, g.x0, g.inv_h, g.gx);
+  const int ya = cell_coord(me.v[1] - reach, g.y0, g.inv_h, g.gy), yb = cell_coord(me.v[1] + reach, g.y0, g.inv_h, g.gy);
+  int count = 0;
+  int64_t out = FILL ? row_ptr[i] : 0;
+  for (int yy = ya; yy <= yb; ++yy) {
+    const int base = g.cell_off + yy * g.gx;
+    const int p0 = cell_start[base + xa], p1 = cell_start[base + xb + 1];
+    for (int p = p0; p < p1; ++p) {
+      if (p == q) continue;
+      Point<T, DIMS> o;
+      o.load(sorted_pts + static_cast<int64_t>(p) * DIMS);
+      if (rdist<DIMS>(me.v, o.v) <= r2) {  // inclusive, like sklearn
+        if (FILL) {
+          edge_index[out] = i;
+          edge_index[n_edges + out] = sorted_idx[p];
+          ++out;
+        }
+        ++count;
+      }
+    }
+  }
+  if (!FILL) row_count[i] = count;
+}
+
+// one thread per row: in-place heapsort of the neighbour ids (rows are short)
+__global__ void __launch_bounds__(128)
+sort_rows_kernel(const int64_t* __restrict__ row_ptr, int64_t n_points, int64_t* __restrict__ cols) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_points) return;
+  int64_t* a = cols + row_ptr[i];
+  const int n = static_cast<int>(row_ptr[i + 1] - row_ptr[i]);
+  if (n < 2) return;
+  if (n <= 24) {  // insertion sort
+    for (int j = 1; j < n; ++j) {
+      const int64_t v = a[j];
+      int m = j - 1;
+      while (m >= 0 && a[m] > v) { a[m + 1] = a[m]; --m; }
+      a[m + 1] = v;
+    }
+    return;
+  }
+  auto sift = [&](int start, int end) {
+    int root = start;
+    while (2 * root + 1 <= end) {
+      int child = 2 * root + 1;
+      if (child + 1 <= end && a[child] < a[child + 1]) ++child;
+      if (a[root] < a[child]) { const int64_t t = a[root]; a[root] = a[child]; a[child] = t; root = child; }
+      else return;
+    }
+  };
+  for (int s = (n - 2) / 2; s >= 0; --s) sift(s, n - 1);
+  for (int end = n - 1; end > 0; --end) {
+    const int64_t t = a[0]; a[0] = a[end]; a[end] = t;
+    sift(0, end - 1);
+  }
+}
+
+// Host -> device upload of a short table through kernel parameters: unlike a pageable
+// cudaMemcpyAsync this never synchronises the stream on the host side.
+struct I64Chunk { int64_t v[24]; };
+__global__ void upload_chunk_kernel(I64Chunk c, int count, int64_t* dst64, int32_t* dst32) {
+  const int i = threadIdx.x;
+  if (i < count) {
+    if (dst64) dst64[i] = c.v[i];
+    if (dst32) dst32[i] = static_cast<int32_t>(c.v[i]);
+  }
+}
+int upload_i64(int64_t* dst64, const int64_t* src_host, int64_t count, cudaStream_t stream, int32_t* dst32 = nullptr) {
+  for (int64_t off = 0; off < count; off += 24) {
+    I64Chunk c;
+    const int m = static_cast<int>(count - off < 24 ? count - off : 24);
+    for (int i = 0; i < m; ++i) c.v[i] = src_host[off + i];
+    upload_chunk_kernel<<<1, 32, 0, stream>>>(c, m, dst64 ? dst64 + off : nullptr, dst32 ? dst32 + off : nullptr);
+    RGNN_LAUNCH_CHECK();
+  }
+  return RGNN_OK;
+}
+
+int host_frame_tables(const int64_t* frame_ptr_host, int32_t n_frames, int32_t k,
+                      int64_t* edge_off, int32_t* cell_off) {
+  int64_t e = 0;
+  int64_t c = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    const int64_t nf = frame_ptr_host[f + 1] - frame_ptr_host[f];
+    if (nf < 0) return RGNN_ERR_INVALID_ARGUMENT;
+    edge_off[f] = e;
+    cell_off[f] = static_cast<int32_t>(c);
+    if (nf > 1 && k > 0) e += nf * k;
+    int64_t target = nf / kPointsPerCell;
+    if (target < 1) target = 1;
+    c += 2 * target + 4;
+  }
+  edge_off[n_frames] = e;
+  cell_off[n_frames] = static_cast<int32_t>(c);
+  return RGNN_OK;
+}
+
+template <typename T>
+int build_cell_lists_t(const T* basis, int32_t dims, const int64_t* frame_ptr_host, int32_t n_frames, int32_t k,
+                       const GraphWorkspace& w, cudaStream_t stream) {
+  const int64_t n = frame_ptr_host[n_frames] - frame_ptr_host[0];
+  RGNN_PROFILE("cell_lists", stream);
+  // small per-frame tables: computed on the host, uploaded without a host-side stream sync
+  {
+    std::vector<int64_t> edge_off(n_frames + 1);
+    std::vector<int32_t> cell_off(n_frames + 1);
+    RGNN_RETURN_IF_ERROR(host_frame_tables(frame_ptr_host, n_frames, k, edge_off.data(), cell_off.data()));
+    if (cell_off[n_frames] > w.total_cells) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+    RGNN_RETURN_IF_ERROR(upload_i64(w.frame_ptr, frame_ptr_host, n_frames + 1, stream));
+    RGNN_RETURN_IF_ERROR(upload_i64(w.frame_edge_off, edge_off.data(), n_frames + 1, stream));
+    std::vector<int64_t> wide(cell_off.begin(), cell_off.end());
+    RGNN_RETURN_IF_ERROR(upload_i64(nullptr, wide.data(), n_frames + 1, stream, w.frame_cell_off));
+  }
+  if (n == 0) return RGNN_OK;
+  init_bbox_kernel<<<div_up(n_frames * 4, 128), 128, 0, stream>>>(w.bbox, n_frames);
+  RGNN_LAUNCH_CHECK();
+  RGNN_CUDA_CHECK(cudaMemsetAsync(w.cell_count, 0, sizeof(int32_t) * (w.total_cells + 1), stream));
+  RGNN_CUDA_CHECK(cudaMemsetAsync(w.cell_cursor, 0, sizeof(int32_t) * (w.total_cells + 1), stream));
+  const unsigned blocks = div_up(n, kThreads);
+  frame_bbox_kernel<T><<<blocks, kThreads, 0, stream>>>(basis, dims, n, w.frame_ptr, n_frames, w.bbox);
+  RGNN_LAUNCH_CHECK();
+  frame_grid_kernel<<<div_up(n_frames, 64), 64, 0, stream>>>(w.bbox, w.frame_ptr, w.frame_edge_off,
+                                                             w.frame_cell_off, n_frames, w.grids);
+  RGNN_LAUNCH_CHECK();
+  bin_count_kernel<T><<<blocks, kThreads, 0, stream>>>(basis, dims, n, w.frame_ptr, n_frames, w.grids,
+                                                       w.point_cell, w.cell_count);
+  RGNN_LAUNCH_CHECK();
+  RGNN_RETURN_IF_ERROR(exclusive_scan_i32(w.cell_count, w.cell_start, w.total_cells, w.scan_scratch, stream));
+  if (dims == 2) {
+    bin_scatter_kernel<T, 2><<<blocks, kThreads, 0, stream>>>(basis, n, w.frame_ptr, n_frames, w.point_cell,
+        w.cell_start, w.cell_cursor, w.sorted_idx, w.sorted_cell, w.sorted_frame, static_cast<T*>(w.sorted_pts));
+  } else {
+    bin_scatter_kernel<T, 4><<<blocks, kThreads, 0, stream>>>(basis, n, w.frame_ptr, n_frames, w.point_cell,
+        w.cell_start, w.cell_cursor, w.sorted_idx, w.sorted_cell, w.sorted_frame, static_cast<T*>(w.sorted_pts));
+  }
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
+}
+
+template <typename T, int DIMS>
+int knn_query_t(int64_t n, int32_t k, int64_t* edge_index, int64_t n_edges, int32_t* in_degree,
+                const GraphWorkspace& w, cudaStream_t stream) {
+  const unsigned blocks = div_up(n, 128);
+  const T* pts = static_cast<const T*>(w.sorted_pts);
+  RGNN_PROFILE("knn_query", stream);
+#define RGNN_KNN_LAUNCH(KMAX)                                                                     \
+  knn_query_kernel<T, DIMS, KMAX><<<blocks, 128, 0, stream>>>(pts, w.sorted_idx, w.sorted_cell,   \
+      w.sorted_frame, w.cell_start, w.grids, n, k, edge_index, n_edges, in_degree)
+  if (k <= 4) RGNN_KNN_LAUNCH(4);
+  else if (k <= 8) RGNN_KNN_LAUNCH(8);
+  else if (k <= 16) RGNN_KNN_LAUNCH(16);
+  else if (k <= 24) RGNN_KNN_LAUNCH(24);
+  else if (k <= 32) RGNN_KNN_LAUNCH(32);
+  else RGNN_KNN_LAUNCH(64);
+#undef RGNN_KNN_LAUNCH
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
+}
+
+template <typename T, int DIMS>
+int radius_query_t(bool fill, int64_t n, double r, int64_t* edge_index, int64_t n_edges,
+                   const GraphWorkspace& w, cudaStream_t stream) {
+  const unsigned blocks = div_up(n, 128);
+  const T* pts = static_cast<const T*>(w.sorted_pts);
+  const double r2 = r * r;  // sklearn: reduced radius = r * r in fp64
+  RGNN_PROFILE("radius_query", stream);
+  if (!fill) {
+    radius_query_kernel<T, DIMS, false><<<blocks, 128, 0, stream>>>(pts, w.sorted_idx, w.sorted_cell,
+        w.sorted_frame, w.cell_start, w.grids, n, r, r2, w.row_count, w.row_ptr, edge_index, n_edges);
+  } else {
+    radius_query_kernel<T, DIMS, true><<<blocks, 128, 0, stream>>>(pts, w.sorted_idx, w.sorted_cell,
+        w.sorted_frame, w.cell_start, w.grids, n, r, r2, w.row_count, w.row_ptr, edge_index, n_edges);
+  }
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
+}
+
+int check_graph_args(const void* basis, int32_t basis_dtype, int32_t dims, const int64_t* frame_ptr_host,
+                     int32_t n_frames, void* workspace, size_t workspace_bytes, int64_t* n_out) {
+  if (frame_ptr_host == nullptr || n_frames < 1) return RGNN_ERR_INVALID_ARGUMENT;
+  if (dims != 2 && dims != 4) return RGNN_ERR_INVALID_ARGUMENT;
+  if (basis_dtype != RGNN_F32 && basis_dtype != RGNN_F64) return RGNN_ERR_INVALID_ARGUMENT;
+  if (frame_ptr_host[0] != 0) return RGNN_ERR_INVALID_ARGUMENT;
+  const int64_t n = frame_ptr_host[n_frames];
+  if (n < 0 || n > 0x7ffffff0LL) return RGNN_ERR_INVALID_ARGUMENT;
+  if (n > 0 && basis == nullptr) return RGNN_ERR_INVALID_ARGUMENT;
+  if (workspace == nullptr || workspace_bytes < rgnn_graph_workspace_bytes(n, n_frames)) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  *n_out = n;
+  return RGNN_OK;
+}
+
+}  // namespace
+
+int build_cell_lists(const void* basis, int32_t basis_dtype, int32_t dims, const int64_t* frame_ptr_host,
+                     int32_t n_frames, int32_t k, const GraphWorkspace& w, cudaStream_t stream) {
+  if (basis_dtype == RGNN_F32)
+    return build_cell_lists_t<float>(static_cast<const float*>(basis), dims, frame_ptr_host, n_frames, k, w, stream);
+  return build_cell_lists_t<double>(static_cast<const double*>(basis), dims, frame_ptr_host, n_frames, k, w, stream);
+}
+
+int knn_query(int32_t basis_dtype, int32_t dims, int64_t n_points, int32_t k, int64_t* edge_index,
+              int64_t n_edges, int32_t* in_degree, const GraphWorkspace& w, cudaStream_t stream) {
+  if (n_points == 0 || n_edges == 0) return RGNN_OK;
+  if (basis_dtype == RGNN_F32) {
+    if (dims == 2) return knn_query_t<float, 2>(n_points, k, edge_index, n_edges, in_degree, w, stream);
+    return knn_query_t<float, 4>(n_points, k, edge_index, n_edges, in_degree, w, stream);
+  }
+  if (dims == 2) return knn_query_t<double, 2>(n_points, k, edge_index, n_edges, in_degree, w, stream);
+  return knn_query_t<double, 4>(n_points, k, edge_index, n_edges, in_degree, w, stream);
+}
+
+static int radius_query(bool fill, int32_t basis_dtype, int32_t dims, int64_t n, double r, int64_t* edge_index,
+                        int64_t n_edges, const GraphWorkspace& w, cudaStream_t stream) {
+  if (basis_dtype == RGNN_F32) {
+    if (dims == 2) return radius_query_t<float, 2>(fill, n, r, edge_index, n_edges, w, stream);
+    return radius_query_t<float, 4>(fill, n, r, edge_index, n_edges, w, stream);
+  }
+  if (dims == 2) return radius_query_t<double, 2>(fill, n, r, edge_index, n_edges, w, stream);
+  return radius_query_t<double, 4>(fill, n, r, edge_index, n_edges, w, stream);
+}
+
+}  // namespace rgnn
+
+using namespace rgnn;
+
+extern "C" {
+
+size_t rgnn_graph_workspace_bytes(int64_t n_points, int32_t n_frames) {
+  if (n_points < 0 || n_frames < 0) return 0;
+  SizeArena a;
+  carve_graph_workspace(a, n_points, n_frames);
+  return a.used;
+}
+
+int64_t rgnn_knn_edge_count(const int64_t* frame_ptr_host, int32_t n_frames, int32_t k, int* status) {
+  int st = RGNN_OK;
+  int64_t e = 0;
+  if (frame_ptr_host == nullptr || n_frames < 0 || k < 1 || k > RGNN_MAX_K) {
+    st = RGNN_ERR_INVALID_ARGUMENT;
+  } else {
+    for (int f = 0; f < n_frames; ++f) {
+      const int64_t nf = frame_ptr_host[f + 1] - frame_ptr_host[f];
+      if (nf < 0) { st = RGNN_ERR_INVALID_ARGUMENT; break; }
+      if (nf > 1) {
+        if (k >= nf) { st = RGNN_ERR_K_NOT_SMALLER_THAN_N; break; }
+        e += nf * k;
+      }
+    }
+  }
+  if (status) *status = st;
+  return st == RGNN_OK ? e : -1;
+}
+
+int rgnn_graph_build_knn(const void* basis, int32_t basis_dtype, int32_t dims, const int64_t* frame_ptr_host,
+                         int32_t n_frames, int32_t k, int64_t* edge_index, int64_t n_edges, void* workspace,
+                         size_t workspace_bytes, rgnn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int64_t n = 0;
+  RGNN_RETURN_IF_ERROR(check_graph_args(basis, basis_dtype, dims, frame_ptr_host, n_frames, workspace, workspace_bytes, &n));
+  int st = RGNN_OK;
+  const int64_t expect = rgnn_knn_edge_count(frame_ptr_host, n_frames, k, &st);
+  if (st != RGNN_OK) return st;
+  if (expect != n_edges || (n_edges > 0 && edge_index == nullptr)) return RGNN_ERR_INVALID_ARGUMENT;
+  Arena arena(workspace, workspace_bytes);
+  GraphWorkspace w = carve_graph_workspace(arena, n, n_frames);
+  if (arena.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  RGNN_RETURN_IF_ERROR(build_cell_lists(basis, basis_dtype, dims, frame_ptr_host, n_frames, k, w, stream));
+  return knn_query(basis_dtype, dims, n, k, edge_index, n_edges, nullptr, w, stream);
+}
+
+int rgnn_graph_build_radius_count(const void* basis, int32_t basis_dtype, int32_t dims,
+                                  const int64_t* frame_ptr_host, int32_t n_frames, double r,
+                                  int64_t* n_edges_host, void* workspace, size_t workspace_bytes,
+                                  rgnn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int64_t n = 0;
+  RGNN_RETURN_IF_ERROR(check_graph_args(basis, basis_dtype, dims, frame_ptr_host, n_frames, workspace, workspace_bytes, &n));
+  if (n_edges_host == nullptr || !(r >= 0.0)) return RGNN_ERR_INVALID_ARGUMENT;
+  Arena arena(workspace, workspace_bytes);
+  GraphWorkspace w = carve_graph_workspace(arena, n, n_frames);
+  if (arena.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  *n_edges_host = 0;
+  RGNN_RETURN_IF_ERROR(build_cell_lists(basis, basis_dtype, dims, frame_ptr_host, n_frames, 0, w, stream));
+  if (n == 0) return RGNN_OK;
+  RGNN_RETURN_IF_ERROR(radius_query(false, basis_dtype, dims, n, r, nullptr, 0, w, stream));
+  RGNN_RETURN_IF_ERROR(exclusive_scan_i32_to_i64(w.row_count, w.row_ptr, n,
+                                                 reinterpret_cast<int64_t*>(w.scan_scratch), stream));
+  RGNN_CUDA_CHECK(cudaMemcpyAsync(n_edges_host, w.row_ptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  RGNN_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return RGNN_OK;
+}
+
+int rgnn_graph_build_radius_fill(const void* basis, int32_t basis_dtype, int32_t dims,
+                                 const int64_t* frame_ptr_host, int32_t n_frames, double r,
+                                 int64_t* edge_index, int64_t n_edges, void* workspace,
+                                 size_t workspace_bytes, rgnn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int64_t n = 0;
+  RGNN_RETURN_IF_ERROR(check_graph_args(basis, basis_dtype, dims, frame_ptr_host, n_frames, workspace, workspace_bytes, &n));
+  if (n_edges < 0 || (n_edges > 0 && edge_index == nullptr)) return RGNN_ERR_INVALID_ARGUMENT;
+  if (n == 0 || n_edges == 0) return RGNN_OK;
+  // the cell lists and row_ptr of the preceding count call are still in the workspace
+  Arena arena(workspace, workspace_bytes);
+  GraphWorkspace w = carve_graph_workspace(arena, n, n_frames);
+  if (arena.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  RGNN_RETURN_IF_ERROR(radius_query(true, basis_dtype, dims, n, r, edge_index, n_edges, w, stream));
+  sort_rows_kernel<<<div_up(n, 128), 128, 0, stream>>>(w.row_ptr, n, edge_index + n_edges);
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
+}
+
+}  // extern "C"

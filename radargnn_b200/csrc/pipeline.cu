@@ -1,0 +1,256 @@
+// pipeline.cu -- the north-star hot path in one call: neighbour search -> edge_index +
+// edge_attr -> CSC view -> L x (graph convolution, training-mode BatchNorm, ReLU).
+// Fuses what the reference runs as two offline/online stages joined by .pt files
+// (preprocessor/radarscenes/dataset_creation.py:187-229 -> gnn/gnn_models.py:124-128).
+#include "conv.cuh"
+#include "csc.cuh"
+#include "features.cuh"
+#include "graph_build.cuh"
+
+namespace rgnn {
+namespace {
+
+struct PipelineWorkspace {
+  GraphWorkspace graph;
+  CscWorkspace csc;
+  float* basis4;       // [N, 4] = [pos | vel] when distance_dims == 4
+  int32_t* csc_ptr;    // [N + 1]
+  int32_t* csc_src;    // [E]
+  int32_t* csc_eid;    // [E]
+  float* ea_csc;       // [E, De]
+  float* h[2];         // [N, c_max] ping-pong layer outputs
+  float* stats;        // [L][3 * c_max]: mean | scale | beta per layer
+  double* bn_scratch;
+  size_t conv_mark;    // arena offset where the per-layer conv workspace starts
+  size_t conv_bytes;   // its size (max over layers)
+};
+
+__global__ void __launch_bounds__(256)
+concat_basis_kernel(const float* __restrict__ pos, const float* __restrict__ vel, int64_t n, float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 p = *reinterpret_cast<const float2*>(pos + i * 2);
+  const float2 v = *reinterpret_cast<const float2*>(vel + i * 2);
+  *reinterpret_cast<float4*>(out + i * 4) = make_float4(p.x, p.y, v.x, v.y);
+}
+
+int validate(const rgnn_pipeline_desc* d, int32_t* de_out, int32_t* c_max_out) {
+  if (d == nullptr || d->layers == nullptr || d->n_layers < 1 || d->n_layers > 64) return RGNN_ERR_INVALID_ARGUMENT;
+  if (d->search != 0 && d->search != 1) return RGNN_ERR_INVALID_ARGUMENT;
+  if (d->distance_dims != 2 && d->distance_dims != 4) return RGNN_ERR_INVALID_ARGUMENT;
+  EdgeFeatureSpec spec;
+  RGNN_RETURN_IF_ERROR(make_edge_feature_spec(d->edge_features, d->n_edge_features, d->edge_mode, &spec));
+  int32_t c_max = 0;
+  for (int l = 0; l < d->n_layers; ++l) {
+    const rgnn_conv_desc& c = d->layers[l];
+    if (c.edge_dim != spec.width) return RGNN_ERR_INVALID_ARGUMENT;
+    if (l > 0 && c.in_channels != d->layers[l - 1].out_channels) return RGNN_ERR_INVALID_ARGUMENT;
+    if (c.out_channels > c_max) c_max = c.out_channels;
+  }
+  *de_out = spec.width;
+  *c_max_out = c_max;
+  return RGNN_OK;
+}
+
+template <typename ArenaT>
+int carve(ArenaT& a, const rgnn_pipeline_desc* d, int64_t n, int32_t n_frames, int64_t e, int32_t de,
+          int32_t c_max, bool with_weights, PipelineWorkspace* w) {
+  w->graph = carve_graph_workspace(a, n, n_frames);
+  w->csc = carve_csc_workspace(a, n);
+  w->basis4 = d->distance_dims == 4 ? a.template take<float>(static_cast<size_t>(n) * 4) : nullptr;
+  w->csc_ptr = a.template take<int32_t>(n + 1);
+  w->csc_src = a.template take<int32_t>(e);
+  w->csc_eid = a.template take<int32_t>(e);
+  w->ea_csc = a.template take<float>(static_cast<size_t>(e) * de);
+  w->h[0] = a.template take<float>(static_cast<size_t>(n) * c_max);
+  w->h[1] = a.template take<float>(static_cast<size_t>(n) * c_max);
+  w->stats = a.template take<float>(static_cast<size_t>(d->n_layers) * 3 * c_max);
+  w->bn_scratch = a.template take<double>(bn_scratch_doubles(n, c_max));
+  w->conv_mark = a.used;
+  size_t worst = 0;
+  for (int l = 0; l < d->n_layers; ++l) {
+    rgnn_conv_desc c = d->layers[l];
+    if (!with_weights) {
+      static const float dummy = 0.f;
+      for (int i = 0; i < RGNN_MAX_MLP_LAYERS; ++i) c.pre_weight[i] = c.pre_bias[i] = c.post_weight[i] = c.post_bias[i] = &dummy;
+      c.edge_encoder_weight = c.edge_encoder_bias = &dummy;
+    }
+    ConvShape s;
+    RGNN_RETURN_IF_ERROR(conv_shape(c, &s));
+    SizeArena sa;
+    sa.used = 0;
+    carve_conv_workspace(sa, c, s, n, e, false);
+    if (sa.used > worst) worst = sa.used;
+  }
+  w->conv_bytes = worst + kAlign;
+  a.template take<char>(w->conv_bytes);
+  return RGNN_OK;
+}
+
+}  // namespace
+}  // namespace rgnn
+
+using namespace rgnn;
+
+extern "C" {
+
+size_t rgnn_pipeline_workspace_bytes(const rgnn_pipeline_desc* desc, int64_t n_points, int32_t n_frames,
+                                     int64_t n_edges) {
+  int32_t de = 0, c_max = 0;
+  if (n_points < 0 || n_frames < 1 || n_edges < 0 || validate(desc, &de, &c_max) != RGNN_OK) return 0;
+  SizeArena a;
+  PipelineWorkspace w;
+  if (carve(a, desc, n_points, n_frames, n_edges, de, c_max, false, &w) != RGNN_OK) return 0;
+  return a.used;
+}
+
+int rgnn_pipeline_forward(const rgnn_pipeline_desc* desc, const float* pos, const float* vel, const float* x0,
+                          const int64_t* frame_ptr_host, int32_t n_frames, int64_t* edge_index, int64_t n_edges,
+                          float* edge_attr, float* h, int32_t* error_flag, void* workspace,
+                          size_t workspace_bytes, rgnn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int32_t de = 0, c_max = 0;
+  RGNN_RETURN_IF_ERROR(validate(desc, &de, &c_max));
+  if (frame_ptr_host == nullptr || n_frames < 1 || frame_ptr_host[0] != 0 || n_edges < 0) return RGNN_ERR_INVALID_ARGUMENT;
+  const int64_t n = frame_ptr_host[n_frames];
+  if (n < 0 || n > 0x7ffffff0LL || n_edges > 0x7ffffff0LL) return RGNN_ERR_INVALID_ARGUMENT;
+  if (error_flag == nullptr) return RGNN_ERR_INVALID_ARGUMENT;
+  if (n > 0 && (pos == nullptr || vel == nullptr || x0 == nullptr || h == nullptr)) return RGNN_ERR_INVALID_ARGUMENT;
+  if (n_edges > 0 && (edge_index == nullptr || (de > 0 && edge_attr == nullptr))) return RGNN_ERR_INVALID_ARGUMENT;
+  if (workspace == nullptr || workspace_bytes < rgnn_pipeline_workspace_bytes(desc, n, n_frames, n_edges))
+    return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  Arena arena(workspace, workspace_bytes);
+  PipelineWorkspace w;
+  RGNN_RETURN_IF_ERROR(carve(arena, desc, n, n_frames, n_edges, de, c_max, true, &w));
+  if (arena.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  RGNN_CUDA_CHECK(cudaMemsetAsync(error_flag, 0, sizeof(int32_t), stream));
+  if (n == 0) return RGNN_OK;
+
+  // ---- 1. neighbour search -> edge_index ---------------------------------------------
+  const float* basis = pos;
+  if (desc->distance_dims == 4) {
+    concat_basis_kernel<<<div_up(n, 256), 256, 0, stream>>>(pos, vel, n, w.basis4);
+    RGNN_LAUNCH_CHECK();
+    basis = w.basis4;
+  }
+  bool counts_ready = false;
+  if (desc->search == 0) {
+    int st = RGNN_OK;
+    const int64_t expect = rgnn_knn_edge_count(frame_ptr_host, n_frames, desc->k, &st);
+    if (st != RGNN_OK) return st;
+    if (expect != n_edges) return RGNN_ERR_INVALID_ARGUMENT;
+    RGNN_RETURN_IF_ERROR(build_cell_lists(basis, RGNN_F32, desc->distance_dims, frame_ptr_host, n_frames, desc->k, w.graph, stream));
+    RGNN_CUDA_CHECK(cudaMemsetAsync(w.csc.count, 0, sizeof(int32_t) * (n + 1), stream));
+    RGNN_RETURN_IF_ERROR(knn_query(RGNN_F32, desc->distance_dims, n, desc->k, edge_index, n_edges, w.csc.count, w.graph, stream));
+    counts_ready = true;
+  } else {
+    // radius: the edge count is data dependent; the caller learned it from
+    // rgnn_graph_build_radius_count, which is repeated here on this workspace (one host sync)
+    int64_t counted = 0;
+    RGNN_RETURN_IF_ERROR(rgnn_graph_build_radius_count(basis, RGNN_F32, desc->distance_dims, frame_ptr_host, n_frames,
+                                                       desc->r, &counted, workspace, workspace_bytes, stream_));
+    if (counted != n_edges) return RGNN_ERR_INVALID_ARGUMENT;
+    RGNN_RETURN_IF_ERROR(rgnn_graph_build_radius_fill(basis, RGNN_F32, desc->distance_dims, frame_ptr_host, n_frames,
+                                                      desc->r, edge_index, n_edges, workspace, workspace_bytes, stream_));
+  }
+
+  // ---- 2. edge attributes ----------------------------------------------------------------
+  EdgeFeatureSpec spec;
+  RGNN_RETURN_IF_ERROR(make_edge_feature_spec(desc->edge_features, desc->n_edge_features, desc->edge_mode, &spec));
+  RGNN_RETURN_IF_ERROR(launch_edge_features(pos, vel, RGNN_F32, 2, 2, edge_index, n_edges, spec, edge_attr, RGNN_F32,
+                                            error_flag, stream));
+
+  // ---- 3. CSC view + edge attributes in slot order -----------------------------------------
+  bool ordered = false;
+  for (int l = 0; l < desc->n_layers; ++l)
+    if (desc->layers[l].aggr == RGNN_AGGR_ADD || desc->layers[l].aggr == RGNN_AGGR_MEAN) ordered = true;
+  RGNN_RETURN_IF_ERROR(csc_build(edge_index, n_edges, n, counts_ready, ordered, w.csc, w.csc_ptr, w.csc_src, w.csc_eid, stream));
+  RGNN_RETURN_IF_ERROR(gather_edge_rows(edge_attr, w.csc_eid, n_edges, de, w.ea_csc, stream));
+
+  // ---- 4. conv -> BatchNorm(train) -> ReLU, L times ------------------------------------------
+  ConvInput in;
+  in.x = x0; in.ldx = desc->layers[0].in_channels;
+  for (int l = 0; l < desc->n_layers; ++l) {
+    const rgnn_conv_desc& c = desc->layers[l];
+    ConvShape s;
+    RGNN_RETURN_IF_ERROR(conv_shape(c, &s));
+    Arena sub(static_cast<char*>(workspace) + w.conv_mark, w.conv_bytes);
+    ConvWorkspace cw = carve_conv_workspace(sub, c, s, n, n_edges, false);
+    if (sub.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+    float* out = w.h[l & 1];
+    RGNN_RETURN_IF_ERROR(conv_forward(c, s, in, n, w.csc_ptr, w.csc_src, nullptr, w.ea_csc, n_edges, out, cw, stream));
+    float* st = w.stats + static_cast<size_t>(l) * 3 * c_max;
+    const float* bw = desc->bn_weight != nullptr ? desc->bn_weight[l] : nullptr;
+    const float* bb = desc->bn_bias != nullptr ? desc->bn_bias[l] : nullptr;
+    RGNN_RETURN_IF_ERROR(bn_statistics(out, s.c_out, n, s.c_out, bw, bb, desc->bn_eps, 0.f, nullptr, nullptr,
+                                       st, st + c_max, st + 2 * c_max, w.bn_scratch, stream));
+    in.x = out; in.ldx = s.c_out;
+    in.mean = st; in.scale = st + c_max; in.beta = st + 2 * c_max; in.relu = 1;
+  }
+  const int32_t c_last = desc->layers[desc->n_layers - 1].out_channels;
+  return bn_apply(in.x, in.ldx, n, c_last, in.mean, in.scale, in.beta, 1, h, c_last, stream);
+}
+
+size_t rgnn_pipeline_host_workspace_bytes(const rgnn_pipeline_desc* desc, int64_t n_points, int32_t n_frames,
+                                          int64_t n_edges, int32_t c0) {
+  int32_t de = 0, c_max = 0;
+  if (n_points < 0 || n_frames < 1 || n_edges < 0 || c0 < 1 || validate(desc, &de, &c_max) != RGNN_OK) return 0;
+  const size_t inner = rgnn_pipeline_workspace_bytes(desc, n_points, n_frames, n_edges);
+  if (inner == 0) return 0;
+  SizeArena a;
+  a.take<float>(static_cast<size_t>(n_points) * 2);
+  a.take<float>(static_cast<size_t>(n_points) * 2);
+  a.take<float>(static_cast<size_t>(n_points) * c0);
+  a.take<int64_t>(static_cast<size_t>(n_edges) * 2);
+  a.take<float>(static_cast<size_t>(n_edges) * de);
+  a.take<float>(static_cast<size_t>(n_points) * desc->layers[desc->n_layers - 1].out_channels);
+  a.take<int32_t>(64);
+  a.take<char>(inner);
+  return a.used;
+}
+
+int rgnn_pipeline_forward_host(const rgnn_pipeline_desc* desc, const float* pos_host, const float* vel_host,
+                               const float* x0_host, int32_t c0, const int64_t* frame_ptr_host, int32_t n_frames,
+                               int64_t* edge_index_host, int64_t n_edges, float* edge_attr_host, float* h_host,
+                               void* workspace, size_t workspace_bytes, rgnn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int32_t de = 0, c_max = 0;
+  RGNN_RETURN_IF_ERROR(validate(desc, &de, &c_max));
+  if (frame_ptr_host == nullptr || n_frames < 1 || n_edges < 0 || c0 != desc->layers[0].in_channels) return RGNN_ERR_INVALID_ARGUMENT;
+  const int64_t n = frame_ptr_host[n_frames];
+  if (n < 0) return RGNN_ERR_INVALID_ARGUMENT;
+  if (n > 0 && (pos_host == nullptr || vel_host == nullptr || x0_host == nullptr)) return RGNN_ERR_INVALID_ARGUMENT;
+  const size_t need = rgnn_pipeline_host_workspace_bytes(desc, n, n_frames, n_edges, c0);
+  if (workspace == nullptr || need == 0 || workspace_bytes < need) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  const int32_t c_last = desc->layers[desc->n_layers - 1].out_channels;
+  Arena a(workspace, workspace_bytes);
+  float* pos = a.take<float>(static_cast<size_t>(n) * 2);
+  float* vel = a.take<float>(static_cast<size_t>(n) * 2);
+  float* x0 = a.take<float>(static_cast<size_t>(n) * c0);
+  int64_t* edge_index = a.take<int64_t>(static_cast<size_t>(n_edges) * 2);
+  float* edge_attr = a.take<float>(static_cast<size_t>(n_edges) * de);
+  float* h = a.take<float>(static_cast<size_t>(n) * c_last);
+  int32_t* flag = a.take<int32_t>(64);
+  const size_t inner = rgnn_pipeline_workspace_bytes(desc, n, n_frames, n_edges);
+  char* inner_ws = a.take<char>(inner);
+  if (a.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  if (n > 0) {
+    RGNN_CUDA_CHECK(cudaMemcpyAsync(pos, pos_host, sizeof(float) * n * 2, cudaMemcpyHostToDevice, stream));
+    RGNN_CUDA_CHECK(cudaMemcpyAsync(vel, vel_host, sizeof(float) * n * 2, cudaMemcpyHostToDevice, stream));
+    RGNN_CUDA_CHECK(cudaMemcpyAsync(x0, x0_host, sizeof(float) * n * c0, cudaMemcpyHostToDevice, stream));
+  }
+  RGNN_RETURN_IF_ERROR(rgnn_pipeline_forward(desc, pos, vel, x0, frame_ptr_host, n_frames, edge_index, n_edges,
+                                             edge_attr, h, flag, inner_ws, inner, stream_));
+  int32_t flag_host = 0;
+  if (edge_index_host != nullptr && n_edges > 0)
+    RGNN_CUDA_CHECK(cudaMemcpyAsync(edge_index_host, edge_index, sizeof(int64_t) * n_edges * 2, cudaMemcpyDeviceToHost, stream));
+  if (edge_attr_host != nullptr && n_edges > 0 && de > 0)
+    RGNN_CUDA_CHECK(cudaMemcpyAsync(edge_attr_host, edge_attr, sizeof(float) * n_edges * de, cudaMemcpyDeviceToHost, stream));
+  if (h_host != nullptr && n > 0)
+    RGNN_CUDA_CHECK(cudaMemcpyAsync(h_host, h, sizeof(float) * n * c_last, cudaMemcpyDeviceToHost, stream));
+  RGNN_CUDA_CHECK(cudaMemcpyAsync(&flag_host, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  RGNN_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return flag_host != 0 ? flag_host : RGNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+"""Mirror of reference graph_constructor/graph.py: ``Graph`` and ``GeometricGraph`` with the same
+attributes and methods, backed by the CUDA neighbour search and feature kernels.
+
+Differences that are deliberate:
+* ``A`` (dense N x N adjacency) is materialised lazily on attribute access -- the reference
+  builds it eagerly with ``toarray()`` (graph.py:59,75), O(N^2) memory;
+* radius graphs list a row's neighbours in ascending column order; the reference inherits
+  sklearn's KD-tree traversal order (same edge set, different order inside a row).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .. import ops
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("radargnn_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class Graph():
+    """General graph (reference graph.py:10-101).
+
+    Attributes: ``X_feat`` node features, ``E_feat`` edge features, ``A`` adjacency matrix,
+    ``E`` edge connection matrix ``[E, 2]`` (column 0 = query point, column 1 = neighbour).
+    """
+
+    def __init__(self):
+        self.X_feat = None
+        self.E_feat = None
+        self._A = None
+        self.E = None
+        self._n = 0
+        self._edge_index_dev: Optional[torch.Tensor] = None  # int64 [2, E] on the device
+
+    # -- adjacency matrix, built only when somebody looks at it ----------------------------------
+    @property
+    def A(self):
+        if self._A is None and self.E is not None:
+            A = np.zeros((self._n, self._n))
+            A[self.E[:, 0], self.E[:, 1]] = 1.0
+            self._A = A
+        return self._A
+
+    @A.setter
+    def A(self, value):
+        self._A = value
+
+    def build(self, X: np.ndarray, routine: str, k: int = 6, r: float = 1) -> None:
+        """Creates the edges between the points ``X`` (all dimensions of ``X`` enter the distance).
+        Nothing is built for fewer than two points or an unknown routine (reference graph.py:45-50)."""
+        X = np.asarray(X)
+        if X.shape[0] > 1:
+            if routine == "knn":
+                self.__build_knn(X, k)
+            elif routine == "radius":
+                self.__build_rn(X, r)
+
+    def __set_edges(self, X: np.ndarray, edge_index: torch.Tensor) -> None:
+        self._n = X.shape[0]
+        self._edge_index_dev = edge_index
+        self.E = edge_index.t().contiguous().cpu().numpy()
+        self._A = None
+
+    def __build_knn(self, X: np.ndarray, k: int) -> None:
+        basis = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64), device=_device())
+        self.__set_edges(X, ops.knn_graph(basis, k))
+
+    def __build_rn(self, X: np.ndarray, r: float) -> None:
+        basis = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64), device=_device())
+        self.__set_edges(X, ops.radius_graph(basis, r))
+
+    def add_node_features(self, feat: np.ndarray) -> None:
+        if self.X_feat is None:
+            self.X_feat = feat
+        else:
+            if feat.shape[0] == self.X_feat.shape[0]:
+                self.X_feat = np.concatenate((self.X_feat, feat), axis=1)
+            else:
+                raise Exception("Feature dimension not compatible")
+
+    def _edge_index(self) -> torch.Tensor:
+        if self._edge_index_dev is None or self._edge_index_dev.shape[1] != self.E.shape[0]:
+            # E was assigned by hand: group rows by source for the degree kernel
+            E = np.asarray(self.E, dtype=np.int64)
+            order = np.lexsort((E[:, 1], E[:, 0]))
+            self._edge_index_dev = torch.as_tensor(np.ascontiguousarray(E[order].T), device=_device())
+            self._n = max(self._n, int(E.max()) + 1 if E.size else 0)
+        return self._edge_index_dev
+
+    def get_degree(self) -> list:
+        """Degree of every node of the undirected graph over ``A`` (reference graph.py:93-96)."""
+        if self.E is None:
+            A = self._A
+            if A is None:
+                raise AttributeError("graph has not been built")
+            rows, cols = np.nonzero(A)
+            self.E = np.stack([rows, cols], axis=1).astype(np.int64)
+            self._n = A.shape[0]
+        n = self._n if self._A is None else self._A.shape[0]
+        deg = ops.undirected_degree(self._edge_index(), n)
+        return [int(v) for v in deg.cpu().tolist()]
+
+    def show(self, node_size: float = 60) -> None:  # pragma: no cover - plotting only
+        import matplotlib.pyplot as plt
+        import networkx as nx
+        G = nx.from_numpy_array(self.A)
+        fig, ax = plt.subplots()
+        nx.draw(G, ax=ax, node_size=node_size)
+
+
+class GeometricGraph(Graph):
+    """Geometric graph separating spatial (``X``), velocity (``V``) and invariant (``F``) node
+    data (reference graph.py:104-302)."""
+
+    def __init__(self):
+        super().__init__()
+        self.X = None
+        self.V = None
+        self.F = None
+
+    def add_invariant_feature(self, name: str, F_add: np.ndarray) -> None:
+        if self.F is None:
+            self.F = {name: F_add}
+        else:
+            self.F[name] = F_add
+
+    def add_degree_to_inv_features(self) -> None:
+        deg = self.get_degree()
+        deg_arr = np.array([deg]).reshape(len(deg), 1)
+        self.add_invariant_feature("degree", deg_arr)
+
+    def extract_node_pair_features(self, features: List[str], edge_mode: str) -> None:
+        """Edge feature matrix ``E_feat`` [E, De] (fp64), columns in list order
+        (reference graph.py:139-223)."""
+        dev = _device()
+        pos = torch.as_tensor(np.ascontiguousarray(self.X, dtype=np.float64), device=dev)
+        vel = torch.as_tensor(np.ascontiguousarray(self.V, dtype=np.float64), device=dev)
+        if self._edge_index_dev is not None and self._edge_index_dev.shape[1] == self.E.shape[0]:
+            ei = self._edge_index_dev
+        else:
+            ei = torch.as_tensor(np.ascontiguousarray(np.asarray(self.E, dtype=np.int64).T), device=dev)
+        feat = ops.edge_features(pos, vel, ei, features, edge_mode, out_dtype=torch.float64)
+        if self.E_feat is None:
+            self.E_feat = np.empty([self.E.shape[0], feat.shape[1]])
+        self.E_feat[:, :] = feat.cpu().numpy()
+
+    def extract_single_node_features(self, features: List[str]) -> None:
+        """Node feature matrix ``X_feat`` [N, Fn], columns in list order (reference graph.py:225-275)."""
+        dev = _device()
+        n = np.asarray(self.X).shape[0]
+        known = [f for f in features if f in ("rcs", "time_index", "degree", "velocity_vector_length",
+                                              "velocity_vector", "spatial_coordinates")]
+        if "degree" in features:
+            self.add_degree_to_inv_features()
+        F = self.F or {}
+
+        def dev_f64(a):
+            return None if a is None else torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64).reshape(n, -1), device=dev)
+
+        deg = F.get("degree")
+        out = ops.node_features(
+            known, n, dev, rcs=dev_f64(F.get("rcs")) if "rcs" in known else None,
+            time_index=dev_f64(F.get("time_index")) if "time_index" in known else None,
+            degree=None if deg is None or "degree" not in known else torch.as_tensor(np.asarray(deg).reshape(-1), device=dev),
+            pos=dev_f64(self.X), vel=dev_f64(self.V), out_dtype=torch.float64)
+        feat = out.cpu().numpy()
+        if feat.shape[1]:
+            self.X_feat = feat if self.X_feat is None else np.concatenate((self.X_feat, feat), axis=1)
+
+    def show(self, *args, **kwargs) -> None:  # pragma: no cover - plotting only
+        super().show(*args, **kwargs)
