@@ -221,6 +221,19 @@ int rgnn_batchnorm_relu_forward(const float* x, int64_t n, int32_t channels,
                                 float* out, void* workspace, size_t workspace_bytes,
                                 rgnn_stream_t stream);
 
+/* Per-channel affine map (+ optional ReLU): out = relu?((x - mean[c]) * scale[c] + beta[c]).
+ * This is BatchNorm in EVAL mode with mean = running_mean, scale = weight / sqrt(running_var + eps),
+ * beta = bias (the reference itself never leaves training mode). */
+int rgnn_affine_relu_forward(const float* x, int64_t n, int32_t channels, const float* mean,
+                             const float* scale, const float* beta, int32_t apply_relu, float* out,
+                             rgnn_stream_t stream);
+
+/* Deterministic sum of `count` floats into *result (DEVICE double): the per-rank loss partial that
+ * the data-parallel step all-reduces.  workspace: rgnn_sum_workspace_bytes(). */
+size_t rgnn_sum_workspace_bytes(void);
+int rgnn_sum_f32(const float* x, int64_t count, double* result, void* workspace, size_t workspace_bytes,
+                 rgnn_stream_t stream);
+
 /* y[n, out] = act(x)[n, in] . W[out, in]^T + b  -- PyG `Linear` (embedding MLPs and heads,
  * gnn/gnn_models.py:137-178).  relu_input applies ReLU to x on load. */
 int rgnn_linear_forward(const float* x, int64_t n, int32_t in_features, const float* weight,

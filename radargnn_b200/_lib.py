@@ -105,6 +105,10 @@ _PROTOTYPES = {
     "rgnn_batchnorm_relu_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                               C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32,
                                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rgnn_affine_relu_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int32, C.c_void_p, C.c_void_p]),
+    "rgnn_sum_workspace_bytes": (C.c_size_t, []),
+    "rgnn_sum_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rgnn_linear_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_void_p, C.c_void_p]),
     "rgnn_pipeline_workspace_bytes": (C.c_size_t, [C.POINTER(PipelineDesc), C.c_int64, C.c_int32, C.c_int64]),

@@ -154,6 +154,39 @@ bn_apply_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int c, cons
   y[r * ldy + ch] = v;
 }
 
+constexpr int kSumBlocks = 592;  // 4 x 148 SMs
+
+__global__ void __launch_bounds__(256)
+sum_partial_kernel(const float* __restrict__ x, int64_t count, double* __restrict__ partial) {
+  __shared__ double warp_sums[8];
+  double s = 0.0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t vec = count >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < vec; i += stride) {
+    const float4 v = x4[i];
+    s += (static_cast<double>(v.x) + static_cast<double>(v.y)) + (static_cast<double>(v.z) + static_cast<double>(v.w));
+  }
+  for (int64_t i = (vec << 2) + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride)
+    s += static_cast<double>(x[i]);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += warp_sums[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void sum_final_kernel(const double* __restrict__ partial, int n, double* __restrict__ result) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < n; ++i) t += partial[i];
+    *result = t;
+  }
+}
+
 }  // namespace
 
 int launch_linear(const LinearArgs& args, cudaStream_t stream) {
@@ -211,6 +244,33 @@ int rgnn_linear_forward(const float* x, int64_t n, int32_t in_features, const fl
   a.y = y; a.ldy = out_features; a.m = n; a.n = out_features;
   a.relu_a1 = relu_input;
   return launch_linear(a, static_cast<cudaStream_t>(stream));
+}
+
+int rgnn_affine_relu_forward(const float* x, int64_t n, int32_t channels, const float* mean, const float* scale,
+                             const float* beta, int32_t apply_relu, float* out, rgnn_stream_t stream) {
+  if (n < 0 || channels < 1) return RGNN_ERR_INVALID_ARGUMENT;
+  if (n == 0) return RGNN_OK;
+  if (x == nullptr || mean == nullptr || scale == nullptr || beta == nullptr || out == nullptr) return RGNN_ERR_INVALID_ARGUMENT;
+  return bn_apply(x, channels, n, channels, mean, scale, beta, apply_relu, out, channels, static_cast<cudaStream_t>(stream));
+}
+
+size_t rgnn_sum_workspace_bytes(void) { return sizeof(double) * kSumBlocks + kAlign; }
+
+int rgnn_sum_f32(const float* x, int64_t count, double* result, void* workspace, size_t workspace_bytes,
+                 rgnn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (count < 0 || result == nullptr || (count > 0 && x == nullptr)) return RGNN_ERR_INVALID_ARGUMENT;
+  if (reinterpret_cast<uintptr_t>(x) % 16 != 0) return RGNN_ERR_INVALID_ARGUMENT;
+  if (workspace == nullptr || workspace_bytes < rgnn_sum_workspace_bytes()) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  Arena arena(workspace, workspace_bytes);
+  double* partial = arena.take<double>(kSumBlocks);
+  if (arena.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  RGNN_PROFILE("loss_sum", stream);
+  sum_partial_kernel<<<kSumBlocks, 256, 0, stream>>>(x, count, partial);
+  RGNN_LAUNCH_CHECK();
+  sum_final_kernel<<<1, 32, 0, stream>>>(partial, kSumBlocks, result);
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
 }
 
 size_t rgnn_batchnorm_workspace_bytes(int64_t n, int32_t channels) {

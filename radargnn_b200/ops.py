@@ -15,7 +15,7 @@ from . import _lib
 
 __all__ = [
     "knn_graph", "radius_graph", "edge_features", "undirected_degree", "node_features", "csc_build",
-    "CscGraph", "ConvParams", "conv_forward", "batchnorm_relu", "linear", "PipelineConfig",
+    "CscGraph", "ConvParams", "conv_forward", "batchnorm_relu", "affine_relu", "sum_f32", "linear", "PipelineConfig",
     "pipeline_forward", "pipeline_forward_host", "knn_edge_count",
 ]
 
@@ -275,6 +275,33 @@ def batchnorm_relu(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Option
             _lib.ptr(None if bias is None else bias.detach()), float(eps), float(momentum),
             _lib.ptr(running_mean), _lib.ptr(running_var), 1 if relu else 0, out.data_ptr(), ws.data_ptr(),
             ws.numel(), _lib.stream_ptr()))
+    return out
+
+
+def affine_relu(x: torch.Tensor, mean: torch.Tensor, scale: torch.Tensor, beta: torch.Tensor, relu: bool) -> torch.Tensor:
+    """out = relu?((x - mean) * scale + beta) per channel (eval-mode BatchNorm)."""
+    _lib.require_device()
+    lib = _lib.load()
+    x = _cuda_contig(x.to(torch.float32), "x")
+    out = torch.empty_like(x)
+    mean, scale, beta = (t.detach().to(torch.float32).contiguous() for t in (mean, scale, beta))
+    with torch.cuda.device(x.device):
+        _lib.check(lib.rgnn_affine_relu_forward(x.data_ptr(), x.shape[0], x.shape[1], mean.data_ptr(),
+                                                scale.data_ptr(), beta.data_ptr(), 1 if relu else 0,
+                                                out.data_ptr(), _lib.stream_ptr()))
+    return out
+
+
+def sum_f32(x: torch.Tensor) -> torch.Tensor:
+    """Deterministic fp64 sum of a float32 tensor, left on the device (double [1])."""
+    _lib.require_device()
+    lib = _lib.load()
+    x = _cuda_contig(x.to(torch.float32), "x")
+    out = torch.empty(1, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        ws = _lib.workspace(lib.rgnn_sum_workspace_bytes(), x.device)
+        _lib.check(lib.rgnn_sum_f32(x.data_ptr(), x.numel(), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    _lib.stream_ptr()))
     return out
 
 
