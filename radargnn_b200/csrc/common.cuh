@@ -156,6 +156,11 @@ size_t bn_scratch_doubles(int64_t n, int32_t c);
 int bn_statistics(const float* x, int64_t ldx, int64_t n, int32_t c, const float* weight, const float* bias,
                   float eps, float momentum, float* running_mean, float* running_var, float* mean,
                   float* scale, float* beta, double* scratch, cudaStream_t stream);
+// Same finalisation from column sums produced elsewhere (node_gemm epilogue): partial[(p*2)*c + ch] =
+// sum, partial[(p*2+1)*c + ch] = sum of squares of partition p.
+int bn_finalize_partials(const double* partial, int64_t n_partials, int64_t n, int32_t c, const float* weight,
+                         const float* bias, float eps, float momentum, float* running_mean, float* running_var,
+                         float* mean, float* scale, float* beta, cudaStream_t stream);
 // y = relu?((x - mean) * scale + beta)
 int bn_apply(const float* x, int64_t ldx, int64_t n, int32_t c, const float* mean, const float* scale,
              const float* beta, int32_t relu, float* y, int64_t ldy, cudaStream_t stream);

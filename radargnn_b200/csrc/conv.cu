@@ -24,6 +24,17 @@ namespace {
 
 constexpr int kAggThreads = 256;
 
+// what a node without incoming edge contributes on the folded tensor-core path (null w_t: nothing)
+struct IsolatedNodeTerm {
+  const float* w_t = nullptr;  // W_pre[:, 0:C], row stride ldw
+  int64_t ldw = 0;
+  const float* x = nullptr;    // layer input rows
+  int64_t ldx = 0;
+  int32_t c = 0;
+  const float* mean = nullptr; const float* scale = nullptr; const float* beta = nullptr;
+  int32_t relu = 0;
+};
+
 // W_e (row-major [p, ldw], rows = output channels) -> shared [de][pp], zero padded
 __device__ __forceinline__ void stage_edge_weights(const float* __restrict__ w_e, int64_t ldw, int p, int pp,
                                                    int de, float* __restrict__ smem) {
@@ -49,7 +60,8 @@ __global__ void __launch_bounds__(kAggThreads)
 edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, int pp, int p,
                       const float* __restrict__ bias, const float* __restrict__ w_e, int64_t ldwe, int de,
                       const float* __restrict__ ea, const int32_t* __restrict__ csc_ptr,
-                      const int32_t* __restrict__ csc_src, int64_t n_nodes, float* __restrict__ out) {
+                      const int32_t* __restrict__ csc_src, int64_t n_nodes, float* __restrict__ out,
+                      IsolatedNodeTerm iso) {
   extern __shared__ float w_s[];  // [de][pp]
   stage_edge_weights(w_e, ldwe, p, pp, de, w_s);
   const int chunks = pp >> 2;
@@ -113,6 +125,21 @@ edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, 
   if (MODE == -1) return;
   const int deg = end - beg;
   float4 r = make_float4(0.f, 0.f, 0.f, 0.f);  // torch_scatter: empty segments aggregate to 0
+  if (deg == 0 && iso.w_t != nullptr) {
+    // Folded formulation (node_gemm.cu): the update weights carry W_m W_t for every node, so a
+    // node without incoming edge cancels that term with M' = -W_t x_n instead of 0.
+    float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* xr = iso.x + node * iso.ldx;
+    for (int i = 0; i < iso.c; ++i) {
+      float xv = xr[i];
+      if (iso.mean != nullptr) xv = (xv - iso.mean[i]) * iso.scale[i] + iso.beta[i];
+      if (iso.relu) xv = fmaxf(xv, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c0 + j < p) acc4[j] = fmaf(iso.w_t[static_cast<int64_t>(c0 + j) * iso.ldw + i], xv, acc4[j]);
+    }
+    r = make_float4(-acc4[0], -acc4[1], -acc4[2], -acc4[3]);
+  }
   if (deg > 0) {
     if (MODE == RGNN_AGGR_MAX || MODE == RGNN_AGGR_MIN) r = add4(base, acc);
     else if (MODE == RGNN_AGGR_ADD) {
@@ -188,7 +215,7 @@ gather_edge_rows_kernel(const float* __restrict__ edge_attr, const int32_t* __re
 template <int MODE>
 int launch_edge_aggregate(const float* a, const float* b, const ConvShape& s, const float* bias, const float* w_e,
                           int64_t ldwe, const float* ea, const int32_t* csc_ptr, const int32_t* csc_src,
-                          int64_t n_nodes, float* out, cudaStream_t stream) {
+                          int64_t n_nodes, float* out, cudaStream_t stream, IsolatedNodeTerm iso = IsolatedNodeTerm()) {
   const int64_t threads = n_nodes * (s.pp >> 2);
   const size_t smem = sizeof(float) * s.de * s.pp;
   RGNN_PROFILE("edge_aggregate", stream);
@@ -196,7 +223,7 @@ int launch_edge_aggregate(const float* a, const float* b, const ConvShape& s, co
     RGNN_CUDA_CHECK(cudaFuncSetAttribute(edge_aggregate_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
   edge_aggregate_kernel<MODE><<<div_up(threads, kAggThreads), kAggThreads, smem, stream>>>(
-      a, b, s.pp, s.p, bias, w_e, ldwe, s.de, ea, csc_ptr, csc_src, n_nodes, out);
+      a, b, s.pp, s.p, bias, w_e, ldwe, s.de, ea, csc_ptr, csc_src, n_nodes, out, iso);
   RGNN_LAUNCH_CHECK();
   return RGNN_OK;
 }
@@ -244,7 +271,8 @@ int gather_edge_rows(const float* edge_attr, const int32_t* csc_eid, int64_t n_e
 
 int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& in, int64_t n_nodes,
                  const int32_t* csc_ptr, const int32_t* csc_src, const int32_t* csc_eid, const float* edge_attr,
-                 int64_t n_edges, float* out, const ConvWorkspace& w, cudaStream_t stream) {
+                 int64_t n_edges, float* out, const ConvWorkspace& w, cudaStream_t stream, int64_t* bn_partials) {
+  if (bn_partials != nullptr) *bn_partials = 0;
   if (n_nodes == 0) return RGNN_OK;
   const bool mpnn = d.conv_type == RGNN_CONV_MPNN;
   const int x_s_off = mpnn ? s.c : 0;            // column block of x_j in W_pre
@@ -267,6 +295,90 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
         w.w_eff, w.b_eff);
     RGNN_LAUNCH_CHECK();
     w_e = w.w_eff; ldwe = s.de; bias = w.b_eff;
+  }
+
+  // ---- tensor-core path: B = x W_s^T, fold W_t through the update, fused BN column sums ---------
+  const bool aligned = (in.ldx % 4 == 0) && (reinterpret_cast<uintptr_t>(in.x) % 16 == 0) &&
+                       (in.mean == nullptr || reinterpret_cast<uintptr_t>(in.mean) % 16 == 0);
+  if (w.tc_post && aligned) {
+    // weight images (weights may have changed since the last call: repacked every forward)
+    TcWeightBlocks wb{};
+    wb.count = 1;
+    wb.block[0] = {d.pre_weight[0] + x_s_off, s.p, s.p, s.c, 0, 0};
+    RGNN_RETURN_IF_ERROR(tc_pack_weights(wb, conv_pre_shape(s), w.wpack_pre, stream));
+    const int64_t ldpost = s.c + s.p;
+    wb.count = 2;
+    wb.block[0] = {d.post_weight[0], ldpost, s.c_out, s.c, 0, 0};
+    wb.block[1] = {d.post_weight[0] + s.c, ldpost, s.c_out, s.p, s.c, 0};
+    const bool third_segment = mpnn && d.aggr == RGNN_AGGR_ADD;
+    if (mpnn) {
+      RGNN_RETURN_IF_ERROR(tc_fold_weights(d.post_weight[0] + s.c, ldpost, d.pre_weight[0], s.p, s.c_out, s.p, s.c,
+                                           w.w_fold, stream));
+      wb.count = 3;
+      if (third_segment) {
+        wb.block[2] = {w.w_fold, s.c, s.c_out, s.c, s.c + s.pp, 0};   // deg * x segment
+      } else {
+        wb.block[2] = {w.w_fold, s.c, s.c_out, s.c, 0, 1};            // added onto W_x: (W_x + W_m W_t) x
+      }
+    }
+    RGNN_RETURN_IF_ERROR(tc_pack_weights(wb, conv_post_shape(d, s), w.wpack_post, stream));
+    RGNN_CUDA_CHECK(cudaMemsetAsync(w.tc_status, 0, sizeof(int32_t), stream));
+
+    TcGemmParams g1;
+    g1.a1 = in.x; g1.lda1 = in.ldx; g1.k1 = s.c;
+    g1.a1_mean = in.mean; g1.a1_scale = in.scale; g1.a1_beta = in.beta; g1.relu_a1 = in.relu;
+    g1.wpack = w.wpack_pre; g1.n = s.p; g1.n_store = s.pp;
+    g1.y = w.b; g1.ldy = s.pp; g1.m = n_nodes; g1.status = w.tc_status;
+    RGNN_RETURN_IF_ERROR(launch_tc_gemm(g1, "node_gemm_pre", stream));
+
+    // M'_n = b + max_e (...) (mean: b + mean; add: deg b + sum): the W_t x_t term is folded into the
+    // update weights.  max / min / mean carry it once per node with an incoming edge, so isolated
+    // nodes cancel it (IsolatedNodeTerm); add carries it deg times (third K segment of the update).
+    IsolatedNodeTerm iso;
+    if (mpnn && d.aggr != RGNN_AGGR_ADD) {
+      iso.w_t = d.pre_weight[0]; iso.ldw = s.p; iso.x = in.x; iso.ldx = in.ldx; iso.c = s.c;
+      iso.mean = in.mean; iso.scale = in.scale; iso.beta = in.beta; iso.relu = in.relu;
+    }
+    switch (d.aggr) {
+      case RGNN_AGGR_MAX: RGNN_RETURN_IF_ERROR(launch_edge_aggregate<RGNN_AGGR_MAX>(nullptr, w.b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, w.m, stream, iso)); break;
+      case RGNN_AGGR_MIN: RGNN_RETURN_IF_ERROR(launch_edge_aggregate<RGNN_AGGR_MIN>(nullptr, w.b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, w.m, stream, iso)); break;
+      case RGNN_AGGR_ADD: RGNN_RETURN_IF_ERROR(launch_edge_aggregate<RGNN_AGGR_ADD>(nullptr, w.b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, w.m, stream, iso)); break;
+      default: RGNN_RETURN_IF_ERROR(launch_edge_aggregate<RGNN_AGGR_MEAN>(nullptr, w.b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, w.m, stream, iso)); break;
+    }
+
+    float* first_out = d.post_layers == 1 ? out : w.t1;
+    TcGemmParams g2;
+    g2.a1 = in.x; g2.lda1 = in.ldx; g2.k1 = s.c;
+    g2.a1_mean = in.mean; g2.a1_scale = in.scale; g2.a1_beta = in.beta; g2.relu_a1 = in.relu;
+    g2.a2 = w.m; g2.lda2 = s.pp; g2.k2 = s.pp;
+    if (third_segment) { g2.k3 = s.c; g2.csc_ptr = csc_ptr; g2.rowscale_mode = 2; }
+    g2.wpack = w.wpack_post; g2.n = s.c_out; g2.n_store = s.c_out; g2.bias = d.post_bias[0];
+    g2.y = first_out; g2.ldy = s.c_out; g2.m = n_nodes; g2.status = w.tc_status;
+    if (!mpnn && d.post_layers == 1) {
+      g2.residual = in.x; g2.ldr = in.ldx;
+      g2.res_mean = in.mean; g2.res_scale = in.scale; g2.res_beta = in.beta; g2.res_relu = in.relu;
+    }
+    if (d.post_layers == 1 && bn_partials != nullptr) {
+      g2.bn_partial = w.bn_partial;
+      *bn_partials = tc_tiles(n_nodes);
+    }
+    RGNN_RETURN_IF_ERROR(launch_tc_gemm(g2, "node_gemm_post", stream));
+    float* cur = first_out;
+    for (int l = 1; l < d.post_layers; ++l) {
+      const bool last = l == d.post_layers - 1;
+      float* nxt = last ? out : (cur == w.t1 ? w.t2 : w.t1);
+      LinearArgs lq;
+      lq.a1 = cur; lq.lda1 = s.c_out; lq.k1 = s.c_out; lq.relu_a1 = 1;
+      lq.w = d.post_weight[l]; lq.ldw = s.c_out; lq.bias = d.post_bias[l];
+      lq.y = nxt; lq.ldy = s.c_out; lq.m = n_nodes; lq.n = s.c_out; lq.tag = "linear_post";
+      if (!mpnn && last) {
+        lq.residual = in.x; lq.ldr = in.ldx;
+        lq.res_mean = in.mean; lq.res_scale = in.scale; lq.res_beta = in.beta; lq.res_relu = in.relu;
+      }
+      RGNN_RETURN_IF_ERROR(launch_linear(lq, stream));
+      cur = nxt;
+    }
+    return RGNN_OK;
   }
 
   // node-level halves of the first message Linear

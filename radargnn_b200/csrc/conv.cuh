@@ -2,6 +2,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "node_gemm.cuh"
 
 namespace rgnn {
 
@@ -32,7 +33,22 @@ struct ConvWorkspace {
   float* ea_csc;   // [E, de] edge attributes in CSC slot order (when csc_eid is given)
   float* u1;       // [E, pp] per-edge activations (general path)
   float* u2;
+  // tensor-core path (node_gemm.cu)
+  bool tc_pre, tc_post;  // which contractions run on tcgen05
+  float* wpack_pre;      // packed W_s image
+  float* wpack_post;     // packed [W_x | W_m | W_fold] image
+  float* w_fold;         // [c_out, c]
+  double* bn_partial;    // [tc_tiles(N)][2][c_out] column sums of the layer output
+  int32_t* tc_status;    // device flag
 };
+
+// shapes of the two node contractions of a layer when they run on the tensor cores
+inline TcGemmShape conv_pre_shape(const ConvShape& s) { TcGemmShape t; t.k1 = s.c; t.n = s.p; return t; }
+inline TcGemmShape conv_post_shape(const rgnn_conv_desc& d, const ConvShape& s) {
+  TcGemmShape t; t.k1 = s.c; t.k2 = s.pp;
+  t.k3 = (d.conv_type == RGNN_CONV_MPNN && d.aggr == RGNN_AGGR_ADD) ? s.c : 0;  // deg * x only for add
+  t.n = s.c_out; return t;
+}
 
 int conv_shape(const rgnn_conv_desc& d, ConvShape* s);
 
@@ -41,7 +57,7 @@ inline ConvWorkspace carve_conv_workspace(ArenaT& a, const rgnn_conv_desc& d, co
                                           int64_t n_nodes, int64_t n_edges, bool need_ea_gather) {
   ConvWorkspace w{};
   const size_t npp = static_cast<size_t>(n_nodes) * s.pp;
-  w.a = d.conv_type == RGNN_CONV_MPNN ? a.template take<float>(npp) : nullptr;
+  w.a = d.conv_type == RGNN_CONV_MPNN ? a.template take<float>(npp) : nullptr;  // unused on the tensor-core path
   w.b = a.template take<float>(npp);
   w.m = a.template take<float>(npp);
   if (d.post_layers > 1) {
@@ -57,6 +73,17 @@ inline ConvWorkspace carve_conv_workspace(ArenaT& a, const rgnn_conv_desc& d, co
     w.u1 = a.template take<float>(static_cast<size_t>(n_edges) * s.pp);
     w.u2 = a.template take<float>(static_cast<size_t>(n_edges) * s.pp);
   }
+  // the factored path puts both node contractions on the tensor cores when their operands fit
+  w.tc_pre = !s.general && tc_gemm_supported(conv_pre_shape(s));
+  w.tc_post = w.tc_pre && tc_gemm_supported(conv_post_shape(d, s));
+  w.tc_pre = w.tc_post;
+  if (w.tc_post) {
+    w.wpack_pre = a.template take<float>(tc_pack_floats(conv_pre_shape(s)));
+    w.wpack_post = a.template take<float>(tc_pack_floats(conv_post_shape(d, s)));
+    w.w_fold = a.template take<float>(static_cast<size_t>(s.c_out) * s.c);
+    w.bn_partial = a.template take<double>(static_cast<size_t>(tc_tiles(n_nodes)) * 2 * s.c_out);
+    w.tc_status = a.template take<int32_t>(64);
+  }
   return w;
 }
 
@@ -65,7 +92,7 @@ inline ConvWorkspace carve_conv_workspace(ArenaT& a, const rgnn_conv_desc& d, co
 int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& in, int64_t n_nodes,
                  const int32_t* csc_ptr, const int32_t* csc_src, const int32_t* csc_eid,
                  const float* edge_attr, int64_t n_edges, float* out, const ConvWorkspace& w,
-                 cudaStream_t stream);
+                 cudaStream_t stream, int64_t* bn_partials = nullptr);
 
 int gather_edge_rows(const float* edge_attr, const int32_t* csc_eid, int64_t n_edges, int32_t de,
                      float* ea_csc, cudaStream_t stream);

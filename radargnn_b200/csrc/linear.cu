@@ -114,18 +114,28 @@ bn_partial_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int c, do
   }
 }
 
+// one block per channel: fixed-assignment strided partial sums + fixed-order tree => deterministic
 __global__ void __launch_bounds__(128)
 bn_finalize_kernel(const double* __restrict__ partial, int n_partials, int64_t n, int c,
                    const float* __restrict__ weight, const float* __restrict__ bias, float eps, float momentum,
                    float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean,
                    float* __restrict__ scale, float* __restrict__ beta) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+  __shared__ double ss[128], sq[128];
+  const int ch = blockIdx.x;
   double s = 0.0, q = 0.0;
-  for (int p = 0; p < n_partials; ++p) {  // fixed order: deterministic
+  for (int p = threadIdx.x; p < n_partials; p += 128) {
     s += partial[(static_cast<int64_t>(p) * 2) * c + ch];
     q += partial[(static_cast<int64_t>(p) * 2 + 1) * c + ch];
   }
+  ss[threadIdx.x] = s;
+  sq[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { ss[threadIdx.x] += ss[threadIdx.x + o]; sq[threadIdx.x] += sq[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  s = ss[0]; q = sq[0];
   const double m = s / static_cast<double>(n);
   double var = q / static_cast<double>(n) - m * m;  // biased, used for the normalisation
   if (var < 0.0) var = 0.0;
@@ -212,8 +222,19 @@ int bn_statistics(const float* x, int64_t ldx, int64_t n, int32_t c, const float
   RGNN_PROFILE("bn_statistics", stream);
   bn_partial_kernel<<<grid, block, 0, stream>>>(x, ldx, n, c, scratch);
   RGNN_LAUNCH_CHECK();
-  bn_finalize_kernel<<<div_up(c, 128), 128, 0, stream>>>(scratch, parts, n, c, weight, bias, eps, momentum,
+  bn_finalize_kernel<<<c, 128, 0, stream>>>(scratch, parts, n, c, weight, bias, eps, momentum,
                                                          running_mean, running_var, mean, scale, beta);
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
+}
+
+int bn_finalize_partials(const double* partial, int64_t n_partials, int64_t n, int32_t c, const float* weight,
+                         const float* bias, float eps, float momentum, float* running_mean, float* running_var,
+                         float* mean, float* scale, float* beta, cudaStream_t stream) {
+  if (n <= 0 || c <= 0) return RGNN_OK;
+  RGNN_PROFILE("bn_statistics", stream);
+  bn_finalize_kernel<<<c, 128, 0, stream>>>(partial, static_cast<int>(n_partials), n, c, weight, bias, eps,
+                                                         momentum, running_mean, running_var, mean, scale, beta);
   RGNN_LAUNCH_CHECK();
   return RGNN_OK;
 }

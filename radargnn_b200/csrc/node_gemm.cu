@@ -1,0 +1,519 @@
+// node_gemm.cu -- the dense node-level contractions on the 5th-generation tensor cores.
+//
+//   y[m, n] = in(A)[m, K] . W[n, K]^T + bias (+ residual)        A = [a1 | a2 | rowscale * a1]
+//
+// used for B = x W_s^T (first message Linear, source half) and for the node update
+// post_mlp([x ; M]) of MPNNConv / RadarPointGNNConv (reference gnn/mpnn_layers.py:89-90, 98-99,
+// 174-175, 181-182).  One persistent CTA per SM, 128-row tiles:
+//   * tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = padded output width, accumulator in TMEM;
+//   * 3xTF32: every fp32 operand is split into hi (top 19 bits) + lo (remainder) and the product is
+//     accumulated as hi*hi + lo*hi + hi*lo in fp32 -- ~2^-21 relative per product, i.e. fp32-grade
+//     results (plain TF32 is ~1e-3 and would miss the reference's 1e-4 parity bar);
+//   * the A operand is produced by the CTA itself (BatchNorm+ReLU of the previous layer applied on
+//     load, hi/lo split), so it is written to shared memory by the threads themselves, in the K-major
+//     128-byte-swizzle layout TMA would produce (full-rate operand fetch; the no-swizzle core-matrix
+//     layout measured 4x slower MMAs), instead of by TMA: raw 32-float K chunks
+//     stream global -> shared through a 3-deep cp.async ring (the stream runs ahead across tiles, so
+//     loads stay in flight during the epilogue), each thread converts the items it loaded itself and
+//     the MMAs of chunk c drain while chunk c+1 is converted;
+//   * W (hi and lo images, packed once per call by pack_weights_kernel) stays resident in shared
+//     memory for all tiles of the CTA;
+//   * epilogue: tcgen05.ld (32 lanes x 16 columns per warp) -> bias / residual -> per-warp staging ->
+//     coalesced stores, plus deterministic per-tile column sums for the BatchNorm statistics.
+#include "node_gemm.cuh"
+
+namespace rgnn {
+namespace {
+
+constexpr int kRows = 128;     // UMMA M
+constexpr int kKc = 32;        // floats of K per chunk (4 MMA k-steps of 8)
+constexpr int kThreads = 256;
+constexpr int kABufFloats = kRows * kKc;  // one hi or lo image of a chunk
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor).  The operand is
+// stored as panels of [rows x 128 bytes] (32 floats of K): row r of an 8-row group sits at r * 128
+// bytes and its 16-byte chunk c at position c ^ (r % 8) (Swizzle<3,4,3>, what TMA's 128B swizzle
+// writes); 8-row groups are SBO = 1024 bytes apart; LBO is unused for swizzled K-major operands.
+// A k-step (8 floats = 32 bytes) is selected by advancing the start address by 32 bytes.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
+  d |= static_cast<uint64_t>(1) << 16;            // LBO (ignored)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;    // SBO
+  d |= static_cast<uint64_t>(1) << 46;            // descriptor version 1 (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;            // layout_type SWIZZLE_128B
+  return d;
+}
+
+// float offset of (row, 16-byte chunk c of the 32-float K block) inside one swizzled panel
+__host__ __device__ __forceinline__ int sw128_offset(int row, int chunk) {
+  return (row >> 3) * 256 + (row & 7) * 32 + ((chunk ^ (row & 7)) << 2);
+}
+
+// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, A and B K-major
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+// bounded wait: a lost arrival must not hang the GPU (returns false on timeout)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (int it = 0; it < (1 << 22); ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return true;
+  }
+  return false;
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  lo = v - hi;  // exact
+}
+
+// ---- weight packing ------------------------------------------------------------------------
+// image = one swizzled [np x 32] panel per 32-float K block, hi image followed by lo image
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(TcWeightBlocks blocks, int np, int kp, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= np * kp) return;   // kp: multiple of 32 here
+  const int nrow = idx / kp, kcol = idx - nrow * kp;
+  float v = 0.f;
+  for (int b = 0; b < blocks.count; ++b) {
+    const TcWeightBlock& wb = blocks.block[b];
+    if (nrow < wb.rows && kcol >= wb.k_offset && kcol < wb.k_offset + wb.cols) {
+      const float t = wb.src[static_cast<int64_t>(nrow) * wb.ld + (kcol - wb.k_offset)];
+      v = wb.accumulate ? v + t : t;
+    }
+  }
+  float hi, lo;
+  split_tf32(v, hi, lo);
+  const int off = (kcol >> 5) * (np * 32) + sw128_offset(nrow, (kcol & 31) >> 2) + (kcol & 3);
+  out[off] = hi;
+  out[np * kp + off] = lo;
+}
+
+// w_fold[c_out, c] = W_m[c_out, p] . W_t[p, c]   (fp64 accumulate): the target-node half of the first
+// message Linear folded through the update Linear
+__global__ void __launch_bounds__(256)
+fold_weights_kernel(const float* __restrict__ w_m, int64_t ld_m, const float* __restrict__ w_t, int64_t ld_t,
+                    int c_out, int p, int c, float* __restrict__ w_fold) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= c_out * c) return;
+  const int o = idx / c, i = idx - o * c;
+  double acc = 0.0;
+  for (int j = 0; j < p; ++j) acc += static_cast<double>(w_m[o * ld_m + j]) * static_cast<double>(w_t[j * ld_t + i]);
+  w_fold[idx] = static_cast<float>(acc);
+}
+
+// ---- the GEMM ------------------------------------------------------------------------------
+constexpr int kRing = 2;  // raw K-chunk slots (cp.async targets), 16 KB each
+
+struct SmemLayout {
+  float* w_hi; float* w_lo;
+  float* a_hi[2]; float* a_lo[2];  // converted chunks (hi / lo images), 1 or 2 stages
+  float* raw;                 // [kRing][128 x 32] chunks as loaded (same swizzled layout)
+  float* col_sum;             // [4][np]
+  float* col_sq;              // [4][np]
+  float* bias;                // [np]
+  uint64_t* bar;              // [2] one per A stage
+  uint32_t* tmem_base;
+};
+
+__device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int np, int kp32, int a_stages) {
+  SmemLayout s;
+  float* f = reinterpret_cast<float*>(base);
+  s.w_hi = f; f += static_cast<size_t>(np) * kp32;
+  s.w_lo = f; f += static_cast<size_t>(np) * kp32;
+  s.a_hi[0] = f; f += kABufFloats;
+  s.a_lo[0] = f; f += kABufFloats;
+  s.a_hi[1] = s.a_hi[0]; s.a_lo[1] = s.a_lo[0];
+  if (a_stages == 2) {
+    s.a_hi[1] = f; f += kABufFloats;
+    s.a_lo[1] = f; f += kABufFloats;
+  }
+  s.raw = f; f += kRing * kABufFloats;
+  s.col_sum = f; f += 4 * np;
+  s.col_sq = f; f += 4 * np;
+  s.bias = f; f += np;
+  s.bar = reinterpret_cast<uint64_t*>(f); f += 4;
+  s.tmem_base = reinterpret_cast<uint32_t*>(f);
+  return s;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+node_gemm_kernel(TcGemmParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int np = p.np, kp = p.kp, kp32 = (p.kp + 31) & ~31;
+  const int a_stages = p.a_stages;
+  const SmemLayout s = carve_smem(smem_raw, np, kp32, a_stages);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tmem_cols = np <= 32 ? 32 : (np <= 64 ? 64 : (np <= 128 ? 128 : 256));
+
+  // ---- one-time setup: barrier, TMEM, resident weights, bias ----------------------------------
+  if (tid == 0) {
+    mbar_init(&s.bar[0], 1);
+    mbar_init(&s.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s.tmem_base)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+
+  // chunk stream of this CTA: chunk g = (tile index g / chunks_per_tile, K offset (g % chunks_per_tile) * 32)
+  const int chunks_per_tile = (kp + kKc - 1) / kKc;
+  const int64_t n_tiles = (p.m + kRows - 1) / kRows;
+  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t my_chunks = my_tiles * chunks_per_tile;
+  const int k_total = p.k1 + p.k2 + p.k3;
+  const int r8 = lane & 7, kq = lane >> 3;
+  const uint32_t raw_addr = smem_u32(s.raw);
+
+  // issue the cp.async loads of this thread's 4 items of chunk g (zero-filled outside the matrix)
+  auto prefetch = [&](int64_t g) {
+    if (g < my_chunks) {
+      const int64_t tile = blockIdx.x + (g / chunks_per_tile) * gridDim.x;
+      const int k0 = static_cast<int>(g % chunks_per_tile) * kKc;
+      const int slot = static_cast<int>(g % kRing);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int u = it * 8 + warp;
+        const int rb = u >> 1, k4 = ((u & 1) << 2) + kq;
+        const int64_t row = tile * kRows + rb * 8 + r8;
+        const int kg = k0 + k4 * 4;
+        const float* src = p.a1;
+        uint32_t bytes = 0;
+        if (row < p.m && kg < k_total) {
+          bytes = 16;
+          if (kg < p.k1) src = p.a1 + row * p.lda1 + kg;
+          else if (kg < p.k1 + p.k2) src = p.a2 + row * p.lda2 + (kg - p.k1);
+          else src = p.a1 + row * p.lda1 + (kg - p.k1 - p.k2);
+        }
+        cp_async16(raw_addr + static_cast<uint32_t>(slot * kABufFloats + rb * 256 + r8 * 32 + ((k4 ^ r8) << 2)) * 4u, src, bytes);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // always commit: uniform group accounting
+  };
+  prefetch(0);
+  prefetch(1);
+
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.wpack);
+    float4* dst = reinterpret_cast<float4*>(s.w_hi);
+    const int total4 = (2 * np * kp32) >> 2;
+    for (int i = tid; i < total4; i += kThreads) dst[i] = src[i];
+    for (int i = tid; i < np; i += kThreads) s.bias[i] = (p.bias != nullptr && i < p.n) ? p.bias[i] : 0.f;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *s.tmem_base;
+  const uint32_t idesc = umma_idesc_tf32(kRows, np);
+  const uint32_t w_hi_addr = smem_u32(s.w_hi), w_lo_addr = smem_u32(s.w_lo);
+  const uint32_t w_panel_bytes = static_cast<uint32_t>(np) * 128u;  // one 32-float K block of W
+  const uint32_t a_hi_addr0 = smem_u32(s.a_hi[0]), a_lo_addr0 = smem_u32(s.a_lo[0]);
+  const uint32_t a_hi_addr1 = smem_u32(s.a_hi[1]), a_lo_addr1 = smem_u32(s.a_lo[1]);
+
+  // per A stage: parity of the next completion to wait for, and whether a commit is outstanding
+  uint32_t phase0 = 0u, phase1 = 0u;
+  bool pending0 = false, pending1 = false;
+  bool timed_out = false;
+  int64_t g = 0;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kRows;
+    for (int k0 = 0; k0 < kp; k0 += kKc, ++g) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  // this thread's items of chunk g have landed
+      const float* raw = s.raw + (g & 1) * kABufFloats;
+      // ---- transform (BatchNorm + ReLU on load, row scale) and hi / lo split, in registers --------
+      float4 hi[4], lo[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int u = it * 8 + warp;
+        const int rb = u >> 1, k4 = ((u & 1) << 2) + kq;
+        const int64_t row = row0 + rb * 8 + r8;
+        const int kg = k0 + k4 * 4;
+        float4 v = *reinterpret_cast<const float4*>(raw + rb * 256 + r8 * 32 + ((k4 ^ r8) << 2));
+        if (row < p.m && kg < k_total) {
+          if (kg < p.k1 || kg >= p.k1 + p.k2) {
+            const int c = kg < p.k1 ? kg : kg - p.k1 - p.k2;
+            if (p.a1_mean != nullptr) {
+              const float4 mu = *reinterpret_cast<const float4*>(p.a1_mean + c);
+              const float4 sc = *reinterpret_cast<const float4*>(p.a1_scale + c);
+              const float4 be = *reinterpret_cast<const float4*>(p.a1_beta + c);
+              v.x = (v.x - mu.x) * sc.x + be.x; v.y = (v.y - mu.y) * sc.y + be.y;
+              v.z = (v.z - mu.z) * sc.z + be.z; v.w = (v.w - mu.w) * sc.w + be.w;
+            }
+            if (p.relu_a1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (kg >= p.k1) {  // third segment: rowscale * a1 (in-degree flag or in-degree)
+              const int deg = p.csc_ptr[row + 1] - p.csc_ptr[row];
+              const float rs = p.rowscale_mode == 2 ? static_cast<float>(deg) : (deg > 0 ? 1.f : 0.f);
+              v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
+            }
+          } else if (p.relu_a2) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          }
+        }
+        split_tf32(v.x, hi[it].x, lo[it].x); split_tf32(v.y, hi[it].y, lo[it].y);
+        split_tf32(v.z, hi[it].z, lo[it].z); split_tf32(v.w, hi[it].w, lo[it].w);
+      }
+      // this thread's raw items are in registers: its slot can take chunk g + 2 right away
+      prefetch(g + 2);
+      // the A stage being overwritten must have been drained by the MMAs that read it
+      const int b = a_stages == 2 ? static_cast<int>(g & 1) : 0;
+      if (b == 0) {
+        if (pending0) { if (!mbar_wait(&s.bar[0], phase0)) timed_out = true; phase0 ^= 1u; pending0 = false; }
+      } else {
+        if (pending1) { if (!mbar_wait(&s.bar[1], phase1)) timed_out = true; phase1 ^= 1u; pending1 = false; }
+      }
+      float* dst_hi = b == 0 ? s.a_hi[0] : s.a_hi[1];
+      float* dst_lo = b == 0 ? s.a_lo[0] : s.a_lo[1];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int u = it * 8 + warp;
+        const int off = (u >> 1) * 256 + r8 * 32 + (((((u & 1) << 2) + kq) ^ r8) << 2);
+        *reinterpret_cast<float4*>(dst_hi + off) = hi[it];
+        *reinterpret_cast<float4*>(dst_lo + off) = lo[it];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (MMA)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      // ---- one thread issues the MMAs of this chunk; they run while the next chunks are converted ---
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int steps = (kp - k0 < kKc ? kp - k0 : kKc) >> 3;
+        const uint32_t a_hi_addr = b == 0 ? a_hi_addr0 : a_hi_addr1, a_lo_addr = b == 0 ? a_lo_addr0 : a_lo_addr1;
+        for (int jj = 0; jj < steps; ++jj) {
+          const int j = (k0 >> 3) + jj;
+          const uint32_t w_off = static_cast<uint32_t>(j >> 2) * w_panel_bytes + static_cast<uint32_t>(j & 3) * 32u;
+          const uint64_t da_hi = umma_desc(a_hi_addr + jj * 32);
+          const uint64_t da_lo = umma_desc(a_lo_addr + jj * 32);
+          const uint64_t dw_hi = umma_desc(w_hi_addr + w_off);
+          const uint64_t dw_lo = umma_desc(w_lo_addr + w_off);
+          umma_tf32(tmem_d, da_hi, dw_hi, idesc, j > 0 ? 1u : 0u);
+          umma_tf32(tmem_d, da_lo, dw_hi, idesc, 1u);
+          umma_tf32(tmem_d, da_hi, dw_lo, idesc, 1u);
+        }
+        umma_commit(b == 0 ? &s.bar[0] : &s.bar[1]);
+      }
+      if (b == 0) pending0 = true; else pending1 = true;
+    }
+    // ---- accumulator complete: the last commit covers every earlier MMA of the tile ---------------
+    {
+      const int b = a_stages == 2 ? static_cast<int>((g - 1) & 1) : 0;
+      if (b == 0) { if (!mbar_wait(&s.bar[0], phase0)) timed_out = true; phase0 ^= 1u; pending0 = false; }
+      else { if (!mbar_wait(&s.bar[1], phase1)) timed_out = true; phase1 ^= 1u; pending1 = false; }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: TMEM -> registers (thread = row, 16 columns) -> bias / residual -> global ----
+    // Each lane stores 4 x 16 bytes of its own row; the column sums for BatchNorm come from a
+    // fixed-order butterfly over the 32 rows of the warp.
+    const int q = warp & 3, half = warp >> 2;
+    const int n_blocks = np >> 4;
+    const int64_t row = row0 + q * 32 + lane;
+    const bool row_ok = row < p.m;
+    const bool vec = ((p.ldy & 3) == 0) && ((p.n_store & 3) == 0) && (p.residual == nullptr || (p.ldr & 3) == 0);
+    float* yrow = p.y + (row_ok ? row : 0) * p.ldy;
+    const float* rrow = p.residual != nullptr ? p.residual + (row_ok ? row : 0) * p.ldr : nullptr;
+    for (int cb = half; cb < n_blocks; cb += 2) {
+      uint32_t r[16];
+      tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(cb * 16), r);
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = cb * 16 + j;
+        v[j] = col < p.n ? __uint_as_float(r[j]) + s.bias[col] : 0.f;
+      }
+      if (rrow != nullptr && row_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = cb * 16 + j;
+          if (col < p.n) {
+            float rv = rrow[col];
+            if (p.res_mean != nullptr) rv = (rv - p.res_mean[col]) * p.res_scale[col] + p.res_beta[col];
+            if (p.res_relu) rv = fmaxf(rv, 0.f);
+            v[j] += rv;
+          }
+        }
+      }
+      if (row_ok) {
+        if (vec) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const int col = cb * 16 + j4 * 4;
+            if (col < p.n_store) *reinterpret_cast<float4*>(yrow + col) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = cb * 16 + j;
+            if (col < p.n_store) yrow[col] = v[j];
+          }
+        }
+      }
+      if (p.bn_partial != nullptr) {
+        // column sums over the warp's 32 rows: butterfly that halves the columns a lane carries
+        float sv[16], sq[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { sv[j] = row_ok ? v[j] : 0.f; sq[j] = sv[j] * sv[j]; }
+#pragma unroll
+        for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+          // lanes with `bit` clear keep columns [0, w), the others keep [w, 2w)
+          const bool upper = (lane & bit) != 0;
+#pragma unroll
+          for (int j = 0; j < w; ++j) {
+            const float send_s = upper ? sv[j] : sv[j + w], keep_s = upper ? sv[j + w] : sv[j];
+            const float send_q = upper ? sq[j] : sq[j + w], keep_q = upper ? sq[j + w] : sq[j];
+            sv[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+            sq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+          }
+        }
+        // lane now holds column cb*16 + (lane >> 1) summed over half the rows (lane parity): finish
+        sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+        sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
+        if ((lane & 1) == 0) {
+          const int col = cb * 16 + (((lane >> 4) & 1) << 3 | ((lane >> 3) & 1) << 2 | ((lane >> 2) & 1) << 1 | ((lane >> 1) & 1));
+          s.col_sum[q * np + col] = sv[0];
+          s.col_sq[q * np + col] = sq[0];
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();  // TMEM drained (the next tile's first MMA overwrites it), column sums complete
+    if (p.bn_partial != nullptr) {
+      for (int c = tid; c < p.n; c += kThreads) {
+        const double sum = (static_cast<double>(s.col_sum[c]) + static_cast<double>(s.col_sum[np + c])) +
+                           (static_cast<double>(s.col_sum[2 * np + c]) + static_cast<double>(s.col_sum[3 * np + c]));
+        const double sq = (static_cast<double>(s.col_sq[c]) + static_cast<double>(s.col_sq[np + c])) +
+                          (static_cast<double>(s.col_sq[2 * np + c]) + static_cast<double>(s.col_sq[3 * np + c]));
+        p.bn_partial[(tile * 2) * p.n + c] = sum;
+        p.bn_partial[(tile * 2 + 1) * p.n + c] = sq;
+      }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+
+  if (timed_out && p.status != nullptr) atomicExch(p.status, RGNN_ERR_CUDA);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+  }
+}
+
+size_t smem_bytes_for(int np, int kp, int a_stages) {
+  const size_t kp32 = (static_cast<size_t>(kp) + 31) & ~static_cast<size_t>(31);
+  return sizeof(float) * (2 * np * kp32 + (2 * a_stages + kRing) * kABufFloats + 8 * np + np + 4 + 4) + 64;
+}
+
+int pick_a_stages(int np, int kp) {
+  if (smem_bytes_for(np, kp, 2) <= 227 * 1024) return 2;
+  if (smem_bytes_for(np, kp, 1) <= 227 * 1024) return 1;
+  return 0;
+}
+
+}  // namespace
+
+bool tc_gemm_supported(const TcGemmShape& sh) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("RGNN_DISABLE_TCGEN05");
+    enabled = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  if (!enabled) return false;
+  if (sh.k1 < 4 || sh.k1 % 4 != 0 || sh.k2 % 4 != 0 || sh.n < 1) return false;
+  const int np = tc_padded_n(sh.n), kp = tc_padded_k(sh.k1 + sh.k2 + sh.k3);
+  if (np > 256) return false;
+  return pick_a_stages(np, kp) > 0;
+}
+
+size_t tc_pack_floats(const TcGemmShape& sh) {
+  return 2 * static_cast<size_t>(tc_padded_n(sh.n)) * ((tc_padded_k(sh.k1 + sh.k2 + sh.k3) + 31) & ~31);
+}
+
+int tc_fold_weights(const float* w_m, int64_t ld_m, const float* w_t, int64_t ld_t, int c_out, int p, int c,
+                    float* w_fold, cudaStream_t stream) {
+  RGNN_PROFILE("weight_prep", stream);
+  fold_weights_kernel<<<div_up(c_out * c, 256), 256, 0, stream>>>(w_m, ld_m, w_t, ld_t, c_out, p, c, w_fold);
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
+}
+
+int tc_pack_weights(const TcWeightBlocks& blocks, const TcGemmShape& sh, float* wpack, cudaStream_t stream) {
+  const int np = tc_padded_n(sh.n), kp = (tc_padded_k(sh.k1 + sh.k2 + sh.k3) + 31) & ~31;
+  RGNN_PROFILE("weight_prep", stream);
+  pack_weights_kernel<<<div_up(np * kp, 256), 256, 0, stream>>>(blocks, np, kp, wpack);
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
+}
+
+int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
+  if (p.m <= 0) return RGNN_OK;
+  p.np = tc_padded_n(p.n);
+  p.kp = tc_padded_k(p.k1 + p.k2 + p.k3);
+  if (p.n_store < p.n) p.n_store = p.n;
+  p.a_stages = pick_a_stages(p.np, p.kp);
+  if (p.a_stages == 0) return RGNN_ERR_UNSUPPORTED;
+  const size_t smem = smem_bytes_for(p.np, p.kp, p.a_stages);
+  static size_t configured = 0;
+  if (smem > configured) {
+    RGNN_CUDA_CHECK(cudaFuncSetAttribute(node_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 227 * 1024;
+  }
+  const int64_t tiles = (p.m + kRows - 1) / kRows;
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  RGNN_PROFILE(tag, stream);
+  node_gemm_kernel<<<grid, kThreads, smem, stream>>>(p);
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
+}
+
+int64_t tc_tiles(int64_t m) { return (m + kRows - 1) / kRows; }
+
+}  // namespace rgnn

@@ -1,0 +1,58 @@
+// node_gemm.cuh -- internal interface of the tcgen05 node contraction (node_gemm.cu).
+#pragma once
+
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace rgnn {
+
+// logical shape of one contraction: K = k1 + k2 + k3 (k3 = 0 or k1: rowscale * a1), N outputs
+struct TcGemmShape {
+  int32_t k1 = 0, k2 = 0, k3 = 0, n = 0;
+};
+
+inline int tc_padded_n(int n) { return (n + 15) & ~15; }
+inline int tc_padded_k(int k) { return (k + 7) & ~7; }
+
+// one block of source weights copied into the packed image: rows x cols of a row-major matrix
+// (row stride ld) placed at K offset k_offset
+struct TcWeightBlock {
+  const float* src;
+  int64_t ld;
+  int32_t rows, cols, k_offset;
+  int32_t accumulate;  // add onto what earlier blocks put at these positions instead of replacing it
+};
+struct TcWeightBlocks {
+  TcWeightBlock block[3];
+  int32_t count;
+};
+
+struct TcGemmParams {
+  const float* a1 = nullptr; int64_t lda1 = 0; int32_t k1 = 0;   // 16-byte aligned rows, k1 % 4 == 0
+  const float* a2 = nullptr; int64_t lda2 = 0; int32_t k2 = 0;   // optional, k2 % 4 == 0
+  int32_t k3 = 0;                                                // 0, or k1: third segment rowscale * a1
+  const int32_t* csc_ptr = nullptr; int32_t rowscale_mode = 0;   // 1: in-degree > 0, 2: in-degree
+  const float* a1_mean = nullptr; const float* a1_scale = nullptr; const float* a1_beta = nullptr;
+  int32_t relu_a1 = 0, relu_a2 = 0;
+  const float* wpack = nullptr;                                  // tc_pack_weights image
+  int32_t n = 0, np = 0, kp = 0, a_stages = 0;
+  const float* bias = nullptr;
+  const float* residual = nullptr; int64_t ldr = 0;
+  const float* res_mean = nullptr; const float* res_scale = nullptr; const float* res_beta = nullptr;
+  int32_t res_relu = 0;
+  float* y = nullptr; int64_t ldy = 0; int32_t n_store = 0;      // columns written (>= n; extras are zeros)
+  double* bn_partial = nullptr;                                  // [tc_tiles(m)][2][n] column sums / squares
+  int64_t m = 0;
+  int32_t* status = nullptr;                                     // device flag set if a barrier wait timed out
+};
+
+bool tc_gemm_supported(const TcGemmShape& sh);
+size_t tc_pack_floats(const TcGemmShape& sh);
+int64_t tc_tiles(int64_t m);
+int tc_fold_weights(const float* w_m, int64_t ld_m, const float* w_t, int64_t ld_t, int c_out, int p, int c,
+                    float* w_fold, cudaStream_t stream);
+int tc_pack_weights(const TcWeightBlocks& blocks, const TcGemmShape& sh, float* wpack, cudaStream_t stream);
+int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream);
+
+}  // namespace rgnn

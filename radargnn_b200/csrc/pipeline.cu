@@ -178,12 +178,20 @@ int rgnn_pipeline_forward(const rgnn_pipeline_desc* desc, const float* pos, cons
     ConvWorkspace cw = carve_conv_workspace(sub, c, s, n, n_edges, false);
     if (sub.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
     float* out = w.h[l & 1];
-    RGNN_RETURN_IF_ERROR(conv_forward(c, s, in, n, w.csc_ptr, w.csc_src, nullptr, w.ea_csc, n_edges, out, cw, stream));
+    int64_t fused_partials = 0;
+    RGNN_RETURN_IF_ERROR(conv_forward(c, s, in, n, w.csc_ptr, w.csc_src, nullptr, w.ea_csc, n_edges, out, cw, stream,
+                                      &fused_partials));
     float* st = w.stats + static_cast<size_t>(l) * 3 * c_max;
     const float* bw = desc->bn_weight != nullptr ? desc->bn_weight[l] : nullptr;
     const float* bb = desc->bn_bias != nullptr ? desc->bn_bias[l] : nullptr;
-    RGNN_RETURN_IF_ERROR(bn_statistics(out, s.c_out, n, s.c_out, bw, bb, desc->bn_eps, 0.f, nullptr, nullptr,
-                                       st, st + c_max, st + 2 * c_max, w.bn_scratch, stream));
+    if (fused_partials > 0) {
+      // the node-update contraction already produced the per-tile column sums
+      RGNN_RETURN_IF_ERROR(bn_finalize_partials(cw.bn_partial, fused_partials, n, s.c_out, bw, bb, desc->bn_eps, 0.f,
+                                                nullptr, nullptr, st, st + c_max, st + 2 * c_max, stream));
+    } else {
+      RGNN_RETURN_IF_ERROR(bn_statistics(out, s.c_out, n, s.c_out, bw, bb, desc->bn_eps, 0.f, nullptr, nullptr,
+                                         st, st + c_max, st + 2 * c_max, w.bn_scratch, stream));
+    }
     in.x = out; in.ldx = s.c_out;
     in.mean = st; in.scale = st + c_max; in.beta = st + 2 * c_max; in.relu = 1;
   }
