@@ -124,6 +124,8 @@ struct LinearArgs {
   const float* a1 = nullptr;   // [m, k1], row stride lda1
   int64_t lda1 = 0;
   int32_t k1 = 0;
+  const int32_t* a1_rows = nullptr;  // optional gather: row r of the input is a1[a1_rows[r]]
+  const int32_t* res_rows = nullptr; // optional gather for the residual rows
   const float* a2 = nullptr;   // optional second K-segment [m, k2]
   int64_t lda2 = 0;
   int32_t k2 = 0;
@@ -162,8 +164,10 @@ int bn_finalize_partials(const double* partial, int64_t n_partials, int64_t n, i
                          const float* bias, float eps, float momentum, float* running_mean, float* running_var,
                          float* mean, float* scale, float* beta, cudaStream_t stream);
 // y = relu?((x - mean) * scale + beta)
+// out_rows (optional): row r is written to y[out_rows[r]] (back to the caller's node order)
 int bn_apply(const float* x, int64_t ldx, int64_t n, int32_t c, const float* mean, const float* scale,
-             const float* beta, int32_t relu, float* y, int64_t ldy, cudaStream_t stream);
+             const float* beta, int32_t relu, float* y, int64_t ldy, cudaStream_t stream,
+             const int32_t* out_rows = nullptr);
 
 }  // namespace rgnn
 

@@ -30,6 +30,7 @@ struct IsolatedNodeTerm {
   int64_t ldw = 0;
   const float* x = nullptr;    // layer input rows
   int64_t ldx = 0;
+  const int32_t* rows = nullptr;
   int32_t c = 0;
   const float* mean = nullptr; const float* scale = nullptr; const float* beta = nullptr;
   int32_t relu = 0;
@@ -55,21 +56,34 @@ __device__ __forceinline__ float4 min4(float4 a, float4 b) { return make_float4(
 
 // One thread per (target node, 4-channel chunk).  MODE: rgnn_aggr, or -1 = write the per-edge
 // activations U[slot] = A[t] + B[s] + W_e e + b instead of reducing (general path).
-template <int MODE>
+// DE > 0: edge-attribute width known at compile time -- the thread's 4 x DE edge weights live in
+// registers and the loop carries no shared-memory traffic; DE == 0: runtime width, weights in smem.
+template <int MODE, int DE>
 __global__ void __launch_bounds__(kAggThreads)
 edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, int pp, int p,
                       const float* __restrict__ bias, const float* __restrict__ w_e, int64_t ldwe, int de,
                       const float* __restrict__ ea, const int32_t* __restrict__ csc_ptr,
                       const int32_t* __restrict__ csc_src, int64_t n_nodes, float* __restrict__ out,
                       IsolatedNodeTerm iso) {
-  extern __shared__ float w_s[];  // [de][pp]
-  stage_edge_weights(w_e, ldwe, p, pp, de, w_s);
+  extern __shared__ float w_s[];  // [de][pp] (DE == 0 only)
+  if (DE == 0) stage_edge_weights(w_e, ldwe, p, pp, de, w_s);
   const int chunks = pp >> 2;
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t node = gid / chunks;
   if (node >= n_nodes) return;
   const int c0 = static_cast<int>(gid - node * chunks) << 2;
   const int beg = csc_ptr[node], end = csc_ptr[node + 1];
+
+  float4 wreg[DE > 0 ? DE : 1];
+  if (DE > 0) {
+#pragma unroll
+    for (int d = 0; d < DE; ++d) {
+      wreg[d].x = c0 + 0 < p ? w_e[static_cast<int64_t>(c0 + 0) * ldwe + d] : 0.f;
+      wreg[d].y = c0 + 1 < p ? w_e[static_cast<int64_t>(c0 + 1) * ldwe + d] : 0.f;
+      wreg[d].z = c0 + 2 < p ? w_e[static_cast<int64_t>(c0 + 2) * ldwe + d] : 0.f;
+      wreg[d].w = c0 + 3 < p ? w_e[static_cast<int64_t>(c0 + 3) * ldwe + d] : 0.f;
+    }
+  }
 
   float4 base = make_float4(0.f, 0.f, 0.f, 0.f);  // A_n + b for this chunk
   if (a != nullptr) base = ld4(a + node * pp + c0);
@@ -88,19 +102,38 @@ edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, 
   else acc = make_float4(0.f, 0.f, 0.f, 0.f);
 
   auto edge_term = [&](int slot, float4 v) {
-    const float* e = ea + static_cast<int64_t>(slot) * de;
-    for (int d = 0; d < de; ++d) v = fma4(e[d], ld4(w_s + d * pp + c0), v);
+    if (DE > 0) {
+      const float* e = ea + static_cast<int64_t>(slot) * DE;
+      if (DE == 2) {
+        const float2 e2 = *reinterpret_cast<const float2*>(e);
+        v = fma4(e2.x, wreg[0], v);
+        v = fma4(e2.y, wreg[DE > 1 ? 1 : 0], v);
+      } else if (DE == 4) {
+        const float4 e4 = *reinterpret_cast<const float4*>(e);
+        v = fma4(e4.x, wreg[0], v);
+        v = fma4(e4.y, wreg[DE > 1 ? 1 : 0], v);
+        v = fma4(e4.z, wreg[DE > 2 ? 2 : 0], v);
+        v = fma4(e4.w, wreg[DE > 3 ? 3 : 0], v);
+      } else {
+#pragma unroll
+        for (int d = 0; d < DE; ++d) v = fma4(e[d], wreg[d], v);
+      }
+    } else {
+      const float* e = ea + static_cast<int64_t>(slot) * de;
+      for (int d = 0; d < de; ++d) v = fma4(e[d], ld4(w_s + d * pp + c0), v);
+    }
     return v;
   };
 
+  const float* bcol = b + c0;
   int slot = beg;
   // 4 gathers in flight per thread
   for (; slot + 4 <= end; slot += 4) {
     const int s0 = csc_src[slot], s1 = csc_src[slot + 1], s2 = csc_src[slot + 2], s3 = csc_src[slot + 3];
-    float4 v0 = ld4(b + static_cast<int64_t>(s0) * pp + c0);
-    float4 v1 = ld4(b + static_cast<int64_t>(s1) * pp + c0);
-    float4 v2 = ld4(b + static_cast<int64_t>(s2) * pp + c0);
-    float4 v3 = ld4(b + static_cast<int64_t>(s3) * pp + c0);
+    float4 v0 = ld4(bcol + static_cast<int64_t>(s0) * pp);
+    float4 v1 = ld4(bcol + static_cast<int64_t>(s1) * pp);
+    float4 v2 = ld4(bcol + static_cast<int64_t>(s2) * pp);
+    float4 v3 = ld4(bcol + static_cast<int64_t>(s3) * pp);
     v0 = edge_term(slot, v0); v1 = edge_term(slot + 1, v1);
     v2 = edge_term(slot + 2, v2); v3 = edge_term(slot + 3, v3);
     if (MODE == RGNN_AGGR_MAX) acc = max4(acc, max4(max4(v0, v1), max4(v2, v3)));
@@ -115,7 +148,7 @@ edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, 
     }
   }
   for (; slot < end; ++slot) {
-    float4 v = ld4(b + static_cast<int64_t>(csc_src[slot]) * pp + c0);
+    float4 v = ld4(bcol + static_cast<int64_t>(csc_src[slot]) * pp);
     v = edge_term(slot, v);
     if (MODE == RGNN_AGGR_MAX) acc = max4(acc, v);
     else if (MODE == RGNN_AGGR_MIN) acc = min4(acc, v);
@@ -129,7 +162,7 @@ edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, 
     // Folded formulation (node_gemm.cu): the update weights carry W_m W_t for every node, so a
     // node without incoming edge cancels that term with M' = -W_t x_n instead of 0.
     float acc4[4] = {0.f, 0.f, 0.f, 0.f};
-    const float* xr = iso.x + node * iso.ldx;
+    const float* xr = iso.x + (iso.rows != nullptr ? static_cast<int64_t>(iso.rows[node]) : node) * iso.ldx;
     for (int i = 0; i < iso.c; ++i) {
       float xv = xr[i];
       if (iso.mean != nullptr) xv = (xv - iso.mean[i]) * iso.scale[i] + iso.beta[i];
@@ -212,20 +245,36 @@ gather_edge_rows_kernel(const float* __restrict__ edge_attr, const int32_t* __re
   ea_csc[idx] = edge_attr[static_cast<int64_t>(csc_eid[slot]) * de + d];
 }
 
+template <int MODE, int DE>
+int launch_edge_aggregate_de(const float* a, const float* b, const ConvShape& s, const float* bias, const float* w_e,
+                             int64_t ldwe, const float* ea, const int32_t* csc_ptr, const int32_t* csc_src,
+                             int64_t n_nodes, float* out, cudaStream_t stream, const IsolatedNodeTerm& iso) {
+  const int64_t threads = n_nodes * (s.pp >> 2);
+  const size_t smem = DE == 0 ? sizeof(float) * s.de * s.pp : 0;
+  if (smem > 48 * 1024)
+    RGNN_CUDA_CHECK(cudaFuncSetAttribute(edge_aggregate_kernel<MODE, DE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+  edge_aggregate_kernel<MODE, DE><<<div_up(threads, kAggThreads), kAggThreads, smem, stream>>>(
+      a, b, s.pp, s.p, bias, w_e, ldwe, s.de, ea, csc_ptr, csc_src, n_nodes, out, iso);
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
+}
+
 template <int MODE>
 int launch_edge_aggregate(const float* a, const float* b, const ConvShape& s, const float* bias, const float* w_e,
                           int64_t ldwe, const float* ea, const int32_t* csc_ptr, const int32_t* csc_src,
                           int64_t n_nodes, float* out, cudaStream_t stream, IsolatedNodeTerm iso = IsolatedNodeTerm()) {
-  const int64_t threads = n_nodes * (s.pp >> 2);
-  const size_t smem = sizeof(float) * s.de * s.pp;
   RGNN_PROFILE("edge_aggregate", stream);
-  if (smem > 48 * 1024)
-    RGNN_CUDA_CHECK(cudaFuncSetAttribute(edge_aggregate_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-  edge_aggregate_kernel<MODE><<<div_up(threads, kAggThreads), kAggThreads, smem, stream>>>(
-      a, b, s.pp, s.p, bias, w_e, ldwe, s.de, ea, csc_ptr, csc_src, n_nodes, out, iso);
-  RGNN_LAUNCH_CHECK();
-  return RGNN_OK;
+  // vector loads of the edge attributes need their natural alignment
+  const bool ea_aligned = (reinterpret_cast<uintptr_t>(ea) % 16) == 0;
+  switch (s.de) {
+    case 1: return launch_edge_aggregate_de<MODE, 1>(a, b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, out, stream, iso);
+    case 2: if (ea_aligned) return launch_edge_aggregate_de<MODE, 2>(a, b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, out, stream, iso); break;
+    case 3: return launch_edge_aggregate_de<MODE, 3>(a, b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, out, stream, iso);
+    case 4: if (ea_aligned) return launch_edge_aggregate_de<MODE, 4>(a, b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, out, stream, iso); break;
+    default: break;
+  }
+  return launch_edge_aggregate_de<MODE, 0>(a, b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, out, stream, iso);
 }
 
 }  // namespace
@@ -325,7 +374,7 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
     RGNN_CUDA_CHECK(cudaMemsetAsync(w.tc_status, 0, sizeof(int32_t), stream));
 
     TcGemmParams g1;
-    g1.a1 = in.x; g1.lda1 = in.ldx; g1.k1 = s.c;
+    g1.a1 = in.x; g1.lda1 = in.ldx; g1.k1 = s.c; g1.a1_rows = in.rows;
     g1.a1_mean = in.mean; g1.a1_scale = in.scale; g1.a1_beta = in.beta; g1.relu_a1 = in.relu;
     g1.wpack = w.wpack_pre; g1.n = s.p; g1.n_store = s.pp;
     g1.y = w.b; g1.ldy = s.pp; g1.m = n_nodes; g1.status = w.tc_status;
@@ -336,7 +385,7 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
     // nodes cancel it (IsolatedNodeTerm); add carries it deg times (third K segment of the update).
     IsolatedNodeTerm iso;
     if (mpnn && d.aggr != RGNN_AGGR_ADD) {
-      iso.w_t = d.pre_weight[0]; iso.ldw = s.p; iso.x = in.x; iso.ldx = in.ldx; iso.c = s.c;
+      iso.w_t = d.pre_weight[0]; iso.ldw = s.p; iso.x = in.x; iso.ldx = in.ldx; iso.c = s.c; iso.rows = in.rows;
       iso.mean = in.mean; iso.scale = in.scale; iso.beta = in.beta; iso.relu = in.relu;
     }
     switch (d.aggr) {
@@ -348,7 +397,7 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
 
     float* first_out = d.post_layers == 1 ? out : w.t1;
     TcGemmParams g2;
-    g2.a1 = in.x; g2.lda1 = in.ldx; g2.k1 = s.c;
+    g2.a1 = in.x; g2.lda1 = in.ldx; g2.k1 = s.c; g2.a1_rows = in.rows;
     g2.a1_mean = in.mean; g2.a1_scale = in.scale; g2.a1_beta = in.beta; g2.relu_a1 = in.relu;
     g2.a2 = w.m; g2.lda2 = s.pp; g2.k2 = s.pp;
     if (third_segment) { g2.k3 = s.c; g2.csc_ptr = csc_ptr; g2.rowscale_mode = 2; }
@@ -372,7 +421,7 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
       lq.w = d.post_weight[l]; lq.ldw = s.c_out; lq.bias = d.post_bias[l];
       lq.y = nxt; lq.ldy = s.c_out; lq.m = n_nodes; lq.n = s.c_out; lq.tag = "linear_post";
       if (!mpnn && last) {
-        lq.residual = in.x; lq.ldr = in.ldx;
+        lq.residual = in.x; lq.ldr = in.ldx; lq.res_rows = in.rows;
         lq.res_mean = in.mean; lq.res_scale = in.scale; lq.res_beta = in.beta; lq.res_relu = in.relu;
       }
       RGNN_RETURN_IF_ERROR(launch_linear(lq, stream));
@@ -383,7 +432,7 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
 
   // node-level halves of the first message Linear
   LinearArgs la;
-  la.a1 = in.x; la.lda1 = in.ldx; la.k1 = s.c;
+  la.a1 = in.x; la.lda1 = in.ldx; la.k1 = s.c; la.a1_rows = in.rows;
   la.a1_mean = in.mean; la.a1_scale = in.scale; la.a1_beta = in.beta; la.relu_a1 = in.relu;
   la.ldw = s.p; la.m = n_nodes; la.n = s.p; la.ldy = s.pp;
   la.tag = "linear_pre_node";
@@ -430,14 +479,14 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
   // node update: post_mlp([x ; M]) (+ x for RadarPointGNNConv)
   float* cur_out = d.post_layers == 1 ? out : w.t1;
   LinearArgs lp;
-  lp.a1 = in.x; lp.lda1 = in.ldx; lp.k1 = s.c;
+  lp.a1 = in.x; lp.lda1 = in.ldx; lp.k1 = s.c; lp.a1_rows = in.rows;
   lp.a1_mean = in.mean; lp.a1_scale = in.scale; lp.a1_beta = in.beta; lp.relu_a1 = in.relu;
   lp.a2 = w.m; lp.lda2 = s.pp; lp.k2 = s.p;
   lp.w = d.post_weight[0]; lp.ldw = s.c + s.p; lp.bias = d.post_bias[0];
   lp.y = cur_out; lp.ldy = s.c_out; lp.m = n_nodes; lp.n = s.c_out;
   lp.tag = "linear_post";
   if (!mpnn && d.post_layers == 1) {
-    lp.residual = in.x; lp.ldr = in.ldx;
+    lp.residual = in.x; lp.ldr = in.ldx; lp.res_rows = in.rows;
     lp.res_mean = in.mean; lp.res_scale = in.scale; lp.res_beta = in.beta; lp.res_relu = in.relu;
   }
   RGNN_RETURN_IF_ERROR(launch_linear(lp, stream));
@@ -450,7 +499,7 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
     lq.y = nxt; lq.ldy = s.c_out; lq.m = n_nodes; lq.n = s.c_out;
     if (!mpnn && last) {
       // residual is the (normalised) layer input, not the intermediate activation
-      lq.residual = in.x; lq.ldr = in.ldx;
+      lq.residual = in.x; lq.ldr = in.ldx; lq.res_rows = in.rows;
       lq.res_mean = in.mean; lq.res_scale = in.scale; lq.res_beta = in.beta; lq.res_relu = in.relu;
     }
     RGNN_RETURN_IF_ERROR(launch_linear(lq, stream));

@@ -11,6 +11,7 @@ namespace rgnn {
 struct ConvInput {
   const float* x = nullptr;  // [N, C]
   int64_t ldx = 0;
+  const int32_t* rows = nullptr;  // optional gather: node r of the layer reads x[rows[r]]
   const float* mean = nullptr;   // [C] or null (no normalisation)
   const float* scale = nullptr;
   const float* beta = nullptr;

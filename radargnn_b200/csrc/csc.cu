@@ -10,20 +10,23 @@ namespace rgnn {
 namespace {
 
 __global__ void __launch_bounds__(256)
-count_targets_kernel(const int64_t* __restrict__ dst, int64_t n_edges, int32_t* __restrict__ count) {
+count_targets_kernel(const int64_t* __restrict__ dst, int64_t n_edges, int32_t* __restrict__ count,
+                     const int32_t* __restrict__ node_map) {
   const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (e < n_edges) atomicAdd(&count[dst[e]], 1);
+  if (e < n_edges) atomicAdd(&count[node_map != nullptr ? node_map[dst[e]] : dst[e]], 1);
 }
 
 __global__ void __launch_bounds__(256)
 fill_slots_kernel(const int64_t* __restrict__ edge_index, int64_t n_edges, const int32_t* __restrict__ csc_ptr,
-                  int32_t* __restrict__ cursor, int32_t* __restrict__ csc_src, int32_t* __restrict__ csc_eid) {
+                  int32_t* __restrict__ cursor, int32_t* __restrict__ csc_src, int32_t* __restrict__ csc_eid,
+                  const int32_t* __restrict__ node_map) {
   const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
-  const int64_t t = edge_index[n_edges + e];
+  int64_t t = edge_index[n_edges + e], s = edge_index[e];
+  if (node_map != nullptr) { t = node_map[t]; s = node_map[s]; }
   const int pos = csc_ptr[t] + atomicAdd(&cursor[t], 1);
   csc_eid[pos] = static_cast<int32_t>(e);
-  csc_src[pos] = static_cast<int32_t>(edge_index[e]);
+  csc_src[pos] = static_cast<int32_t>(s);
 }
 
 // one thread per target: order the segment by edge id (segments are short: in-degree)
@@ -65,19 +68,19 @@ sort_segments_kernel(const int32_t* __restrict__ csc_ptr, int64_t n_nodes, int32
 
 int csc_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, bool counts_ready,
               bool ordered, const CscWorkspace& w, int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid,
-              cudaStream_t stream) {
+              cudaStream_t stream, const int32_t* node_map) {
   RGNN_PROFILE("csc_build", stream);
   if (!counts_ready) {
     RGNN_CUDA_CHECK(cudaMemsetAsync(w.count, 0, sizeof(int32_t) * (n_nodes + 1), stream));
     if (n_edges > 0) {
-      count_targets_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index + n_edges, n_edges, w.count);
+      count_targets_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index + n_edges, n_edges, w.count, node_map);
       RGNN_LAUNCH_CHECK();
     }
   }
   RGNN_RETURN_IF_ERROR(exclusive_scan_i32(w.count, csc_ptr, n_nodes, w.scan_scratch, stream));
   if (n_edges == 0) return RGNN_OK;
   RGNN_CUDA_CHECK(cudaMemsetAsync(w.cursor, 0, sizeof(int32_t) * (n_nodes + 1), stream));
-  fill_slots_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index, n_edges, csc_ptr, w.cursor, csc_src, csc_eid);
+  fill_slots_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index, n_edges, csc_ptr, w.cursor, csc_src, csc_eid, node_map);
   RGNN_LAUNCH_CHECK();
   if (ordered) {
     sort_segments_kernel<<<div_up(n_nodes, 128), 128, 0, stream>>>(csc_ptr, n_nodes, csc_src, csc_eid);

@@ -22,7 +22,10 @@ inline CscWorkspace carve_csc_workspace(ArenaT& a, int64_t n_nodes) {
 
 // counts_ready: w.count already holds the in-degree histogram; ordered: sort every segment by
 // edge id (needed for a deterministic sum / mean; max / min do not care).
+// node_map (optional): targets and sources are renumbered through node_map[] (the conv stack runs in
+// cell-sorted node order); csc_eid always refers to the caller's edge order.
 int csc_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, bool counts_ready, bool ordered,
-              const CscWorkspace& w, int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid, cudaStream_t stream);
+              const CscWorkspace& w, int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid, cudaStream_t stream,
+              const int32_t* node_map = nullptr);
 
 }  // namespace rgnn

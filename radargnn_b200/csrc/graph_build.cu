@@ -141,22 +141,64 @@ bin_count_kernel(const T* __restrict__ basis, int dims, int64_t n, const int64_t
   atomicAdd(&cell_count[cell], 1);
 }
 
-template <typename T, int DIMS>
+// counting-sort scatter: only the ids; the order inside a cell is made deterministic afterwards
 __global__ void __launch_bounds__(kThreads)
-bin_scatter_kernel(const T* __restrict__ basis, int64_t n, const int64_t* __restrict__ frame_ptr, int n_frames,
-                   const int32_t* __restrict__ point_cell, const int32_t* __restrict__ cell_start,
-                   int32_t* __restrict__ cell_cursor, int32_t* __restrict__ sorted_idx,
-                   int32_t* __restrict__ sorted_cell, int32_t* __restrict__ sorted_frame,
-                   T* __restrict__ sorted_pts) {
+bin_scatter_kernel(int64_t n, const int32_t* __restrict__ point_cell, const int32_t* __restrict__ cell_start,
+                   int32_t* __restrict__ cell_cursor, int32_t* __restrict__ sorted_idx) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int cell = point_cell[i];
-  const int pos = cell_start[cell] + atomicAdd(&cell_cursor[cell], 1);
-  sorted_idx[pos] = static_cast<int32_t>(i);
-  sorted_cell[pos] = cell;
+  sorted_idx[cell_start[cell] + atomicAdd(&cell_cursor[cell], 1)] = static_cast<int32_t>(i);
+}
+
+// one thread per cell: ascending point id inside the cell, so that the cell-sorted order (and with it
+// every reduction order downstream) does not depend on the atomics' arrival order
+__global__ void __launch_bounds__(128)
+cell_sort_kernel(const int32_t* __restrict__ cell_start, int total_cells, int32_t* __restrict__ sorted_idx) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= total_cells) return;
+  int32_t* a = sorted_idx + cell_start[c];
+  const int n = cell_start[c + 1] - cell_start[c];
+  if (n < 2) return;
+  if (n <= 32) {
+    for (int j = 1; j < n; ++j) {
+      const int32_t v = a[j];
+      int m = j - 1;
+      while (m >= 0 && a[m] > v) { a[m + 1] = a[m]; --m; }
+      a[m + 1] = v;
+    }
+    return;
+  }
+  auto sift = [&](int start, int end) {
+    int root = start;
+    while (2 * root + 1 <= end) {
+      int child = 2 * root + 1;
+      if (child + 1 <= end && a[child] < a[child + 1]) ++child;
+      if (a[root] < a[child]) { const int32_t t = a[root]; a[root] = a[child]; a[child] = t; root = child; }
+      else return;
+    }
+  };
+  for (int s = (n - 2) / 2; s >= 0; --s) sift(s, n - 1);
+  for (int end = n - 1; end > 0; --end) {
+    const int32_t t = a[0]; a[0] = a[end]; a[end] = t;
+    sift(0, end - 1);
+  }
+}
+
+template <typename T, int DIMS>
+__global__ void __launch_bounds__(kThreads)
+gather_sorted_kernel(const T* __restrict__ basis, int64_t n, const int64_t* __restrict__ frame_ptr, int n_frames,
+                     const int32_t* __restrict__ point_cell, const int32_t* __restrict__ sorted_idx,
+                     int32_t* __restrict__ sorted_cell, int32_t* __restrict__ sorted_frame,
+                     int32_t* __restrict__ rank, T* __restrict__ sorted_pts) {
+  const int64_t pos = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pos >= n) return;
+  const int64_t i = sorted_idx[pos];
+  rank[i] = static_cast<int32_t>(pos);
+  sorted_cell[pos] = point_cell[i];
   sorted_frame[pos] = n_frames == 1 ? 0 : find_frame(frame_ptr, n_frames, i);
 #pragma unroll
-  for (int d = 0; d < DIMS; ++d) sorted_pts[static_cast<int64_t>(pos) * DIMS + d] = basis[i * DIMS + d];
+  for (int d = 0; d < DIMS; ++d) sorted_pts[pos * DIMS + d] = basis[i * DIMS + d];
 }
 
 // ---- exact reduced distance ---------------------------------------------------------
@@ -203,7 +245,7 @@ knn_query_kernel(const T* __restrict__ sorted_pts, const int32_t* __restrict__ s
                  const int32_t* __restrict__ sorted_cell, const int32_t* __restrict__ sorted_frame,
                  const int32_t* __restrict__ cell_start, const FrameGrid* __restrict__ grids,
                  int64_t n_points, int k, int64_t* __restrict__ edge_index, int64_t n_edges,
-                 int32_t* __restrict__ in_degree) {
+                 int32_t* __restrict__ in_degree, const int32_t* __restrict__ degree_map) {
   const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (q >= n_points) return;
   const FrameGrid g = grids[sorted_frame[q]];
@@ -285,7 +327,7 @@ knn_query_kernel(const T* __restrict__ sorted_pts, const int32_t* __restrict__ s
     if (j < k) {  // slot j is the (k-1-j)-th nearest
       edge_index[e0 + (k - 1 - j)] = i;
       edge_index[n_edges + e0 + (k - 1 - j)] = bi[j];
-      if (in_degree != nullptr) atomicAdd(&in_degree[bi[j]], 1);
+      if (in_degree != nullptr) atomicAdd(&in_degree[degree_map != nullptr ? degree_map[bi[j]] : bi[j]], 1);
     }
   }
 }
@@ -435,12 +477,16 @@ int build_cell_lists_t(const T* basis, int32_t dims, const int64_t* frame_ptr_ho
                                                        w.point_cell, w.cell_count);
   RGNN_LAUNCH_CHECK();
   RGNN_RETURN_IF_ERROR(exclusive_scan_i32(w.cell_count, w.cell_start, w.total_cells, w.scan_scratch, stream));
+  bin_scatter_kernel<<<blocks, kThreads, 0, stream>>>(n, w.point_cell, w.cell_start, w.cell_cursor, w.sorted_idx);
+  RGNN_LAUNCH_CHECK();
+  cell_sort_kernel<<<div_up(w.total_cells, 128), 128, 0, stream>>>(w.cell_start, w.total_cells, w.sorted_idx);
+  RGNN_LAUNCH_CHECK();
   if (dims == 2) {
-    bin_scatter_kernel<T, 2><<<blocks, kThreads, 0, stream>>>(basis, n, w.frame_ptr, n_frames, w.point_cell,
-        w.cell_start, w.cell_cursor, w.sorted_idx, w.sorted_cell, w.sorted_frame, static_cast<T*>(w.sorted_pts));
+    gather_sorted_kernel<T, 2><<<blocks, kThreads, 0, stream>>>(basis, n, w.frame_ptr, n_frames, w.point_cell,
+        w.sorted_idx, w.sorted_cell, w.sorted_frame, w.rank, static_cast<T*>(w.sorted_pts));
   } else {
-    bin_scatter_kernel<T, 4><<<blocks, kThreads, 0, stream>>>(basis, n, w.frame_ptr, n_frames, w.point_cell,
-        w.cell_start, w.cell_cursor, w.sorted_idx, w.sorted_cell, w.sorted_frame, static_cast<T*>(w.sorted_pts));
+    gather_sorted_kernel<T, 4><<<blocks, kThreads, 0, stream>>>(basis, n, w.frame_ptr, n_frames, w.point_cell,
+        w.sorted_idx, w.sorted_cell, w.sorted_frame, w.rank, static_cast<T*>(w.sorted_pts));
   }
   RGNN_LAUNCH_CHECK();
   return RGNN_OK;
@@ -448,13 +494,13 @@ int build_cell_lists_t(const T* basis, int32_t dims, const int64_t* frame_ptr_ho
 
 template <typename T, int DIMS>
 int knn_query_t(int64_t n, int32_t k, int64_t* edge_index, int64_t n_edges, int32_t* in_degree,
-                const GraphWorkspace& w, cudaStream_t stream) {
+                const int32_t* degree_map, const GraphWorkspace& w, cudaStream_t stream) {
   const unsigned blocks = div_up(n, 128);
   const T* pts = static_cast<const T*>(w.sorted_pts);
   RGNN_PROFILE("knn_query", stream);
 #define RGNN_KNN_LAUNCH(KMAX)                                                                     \
   knn_query_kernel<T, DIMS, KMAX><<<blocks, 128, 0, stream>>>(pts, w.sorted_idx, w.sorted_cell,   \
-      w.sorted_frame, w.cell_start, w.grids, n, k, edge_index, n_edges, in_degree)
+      w.sorted_frame, w.cell_start, w.grids, n, k, edge_index, n_edges, in_degree, degree_map)
   if (k <= 4) RGNN_KNN_LAUNCH(4);
   else if (k <= 8) RGNN_KNN_LAUNCH(8);
   else if (k <= 16) RGNN_KNN_LAUNCH(16);
@@ -508,14 +554,15 @@ int build_cell_lists(const void* basis, int32_t basis_dtype, int32_t dims, const
 }
 
 int knn_query(int32_t basis_dtype, int32_t dims, int64_t n_points, int32_t k, int64_t* edge_index,
-              int64_t n_edges, int32_t* in_degree, const GraphWorkspace& w, cudaStream_t stream) {
+              int64_t n_edges, int32_t* in_degree, const int32_t* degree_map, const GraphWorkspace& w,
+              cudaStream_t stream) {
   if (n_points == 0 || n_edges == 0) return RGNN_OK;
   if (basis_dtype == RGNN_F32) {
-    if (dims == 2) return knn_query_t<float, 2>(n_points, k, edge_index, n_edges, in_degree, w, stream);
-    return knn_query_t<float, 4>(n_points, k, edge_index, n_edges, in_degree, w, stream);
+    if (dims == 2) return knn_query_t<float, 2>(n_points, k, edge_index, n_edges, in_degree, degree_map, w, stream);
+    return knn_query_t<float, 4>(n_points, k, edge_index, n_edges, in_degree, degree_map, w, stream);
   }
-  if (dims == 2) return knn_query_t<double, 2>(n_points, k, edge_index, n_edges, in_degree, w, stream);
-  return knn_query_t<double, 4>(n_points, k, edge_index, n_edges, in_degree, w, stream);
+  if (dims == 2) return knn_query_t<double, 2>(n_points, k, edge_index, n_edges, in_degree, degree_map, w, stream);
+  return knn_query_t<double, 4>(n_points, k, edge_index, n_edges, in_degree, degree_map, w, stream);
 }
 
 static int radius_query(bool fill, int32_t basis_dtype, int32_t dims, int64_t n, double r, int64_t* edge_index,
@@ -574,7 +621,7 @@ int rgnn_graph_build_knn(const void* basis, int32_t basis_dtype, int32_t dims, c
   GraphWorkspace w = carve_graph_workspace(arena, n, n_frames);
   if (arena.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
   RGNN_RETURN_IF_ERROR(build_cell_lists(basis, basis_dtype, dims, frame_ptr_host, n_frames, k, w, stream));
-  return knn_query(basis_dtype, dims, n, k, edge_index, n_edges, nullptr, w, stream);
+  return knn_query(basis_dtype, dims, n, k, edge_index, n_edges, nullptr, nullptr, w, stream);
 }
 
 int rgnn_graph_build_radius_count(const void* basis, int32_t basis_dtype, int32_t dims,

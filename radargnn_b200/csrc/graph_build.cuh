@@ -34,6 +34,7 @@ struct GraphWorkspace {
   int32_t* sorted_idx;     // [N] original point id at each sorted position
   int32_t* sorted_cell;    // [N]
   int32_t* sorted_frame;   // [N]
+  int32_t* rank;           // [N] sorted position of every original point (inverse of sorted_idx)
   void* sorted_pts;        // [N, dims] of the basis dtype, cell-sorted
   int32_t* row_count;      // [N + 1] radius: neighbours per point (original order)
   int64_t* row_ptr;        // [N + 1] radius: exclusive scan
@@ -60,6 +61,7 @@ inline GraphWorkspace carve_graph_workspace(ArenaT& a, int64_t n, int32_t f) {
   w.sorted_idx = a.template take<int32_t>(n);
   w.sorted_cell = a.template take<int32_t>(n);
   w.sorted_frame = a.template take<int32_t>(n);
+  w.rank = a.template take<int32_t>(n);
   w.sorted_pts = a.template take<double>(static_cast<size_t>(n) * 4);
   w.row_count = a.template take<int32_t>(n + 1);
   w.row_ptr = a.template take<int64_t>(n + 1);
@@ -76,8 +78,10 @@ int build_cell_lists(const void* basis, int32_t basis_dtype, int32_t dims,
 
 // k-NN query over the cell lists.  Optional fused outputs (may be null): in-degree
 // histogram of the targets (edge_index[1]) for the CSC build.
+// degree_map (optional): the histogram is indexed by degree_map[target] (the conv stack runs in
+// cell-sorted node order, degree_map = rank).
 int knn_query(int32_t basis_dtype, int32_t dims, int64_t n_points, int32_t k,
-              int64_t* edge_index, int64_t n_edges, int32_t* in_degree,
+              int64_t* edge_index, int64_t n_edges, int32_t* in_degree, const int32_t* degree_map,
               const GraphWorkspace& w, cudaStream_t stream);
 
 }  // namespace rgnn

@@ -38,7 +38,7 @@ linear_kernel(LinearArgs p) {
       float v = 0.f;
       if (row < p.m && kg < K) {
         if (kg < p.k1) {
-          v = p.a1[row * p.lda1 + kg];
+          v = p.a1[(p.a1_rows != nullptr ? p.a1_rows[row] : row) * p.lda1 + kg];
           if (p.a1_mean != nullptr) v = (v - p.a1_mean[kg]) * p.a1_scale[kg] + p.a1_beta[kg];
           if (p.relu_a1) v = fmaxf(v, 0.f);
         } else {
@@ -75,7 +75,7 @@ linear_kernel(LinearArgs p) {
       float v = acc[i][j];
       if (p.bias != nullptr) v += p.bias[col];
       if (p.residual != nullptr) {
-        float r = p.residual[row * p.ldr + col];
+        float r = p.residual[(p.res_rows != nullptr ? p.res_rows[row] : row) * p.ldr + col];
         if (p.res_mean != nullptr) r = (r - p.res_mean[col]) * p.res_scale[col] + p.res_beta[col];
         if (p.res_relu) r = fmaxf(r, 0.f);
         v += r;
@@ -154,14 +154,14 @@ bn_finalize_kernel(const double* __restrict__ partial, int n_partials, int64_t n
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int c, const float* __restrict__ mean,
                 const float* __restrict__ scale, const float* __restrict__ beta, int relu,
-                float* __restrict__ y, int64_t ldy) {
+                float* __restrict__ y, int64_t ldy, const int32_t* __restrict__ out_rows) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= n * c) return;
   const int64_t r = idx / c;
   const int ch = static_cast<int>(idx - r * c);
   float v = (x[r * ldx + ch] - mean[ch]) * scale[ch] + beta[ch];
   if (relu) v = fmaxf(v, 0.f);
-  y[r * ldy + ch] = v;
+  y[(out_rows != nullptr ? out_rows[r] : r) * ldy + ch] = v;
 }
 
 constexpr int kSumBlocks = 592;  // 4 x 148 SMs
@@ -240,10 +240,10 @@ int bn_finalize_partials(const double* partial, int64_t n_partials, int64_t n, i
 }
 
 int bn_apply(const float* x, int64_t ldx, int64_t n, int32_t c, const float* mean, const float* scale,
-             const float* beta, int32_t relu, float* y, int64_t ldy, cudaStream_t stream) {
+             const float* beta, int32_t relu, float* y, int64_t ldy, cudaStream_t stream, const int32_t* out_rows) {
   if (n <= 0 || c <= 0) return RGNN_OK;
   RGNN_PROFILE("bn_apply", stream);
-  bn_apply_kernel<<<div_up(n * c, 256), 256, 0, stream>>>(x, ldx, n, c, mean, scale, beta, relu, y, ldy);
+  bn_apply_kernel<<<div_up(n * c, 256), 256, 0, stream>>>(x, ldx, n, c, mean, scale, beta, relu, y, ldy, out_rows);
   RGNN_LAUNCH_CHECK();
   return RGNN_OK;
 }

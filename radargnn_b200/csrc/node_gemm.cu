@@ -228,9 +228,12 @@ node_gemm_kernel(TcGemmParams p) {
         uint32_t bytes = 0;
         if (row < p.m && kg < k_total) {
           bytes = 16;
-          if (kg < p.k1) src = p.a1 + row * p.lda1 + kg;
-          else if (kg < p.k1 + p.k2) src = p.a2 + row * p.lda2 + (kg - p.k1);
-          else src = p.a1 + row * p.lda1 + (kg - p.k1 - p.k2);
+          if (kg >= p.k1 && kg < p.k1 + p.k2) {
+            src = p.a2 + row * p.lda2 + (kg - p.k1);
+          } else {
+            const int64_t arow = p.a1_rows != nullptr ? p.a1_rows[row] : row;
+            src = p.a1 + arow * p.lda1 + (kg < p.k1 ? kg : kg - p.k1 - p.k2);
+          }
         }
         cp_async16(raw_addr + static_cast<uint32_t>(slot * kABufFloats + rb * 256 + r8 * 32 + ((k4 ^ r8) << 2)) * 4u, src, bytes);
       }
@@ -359,7 +362,8 @@ node_gemm_kernel(TcGemmParams p) {
     const bool row_ok = row < p.m;
     const bool vec = ((p.ldy & 3) == 0) && ((p.n_store & 3) == 0) && (p.residual == nullptr || (p.ldr & 3) == 0);
     float* yrow = p.y + (row_ok ? row : 0) * p.ldy;
-    const float* rrow = p.residual != nullptr ? p.residual + (row_ok ? row : 0) * p.ldr : nullptr;
+    const float* rrow = p.residual != nullptr
+        ? p.residual + (row_ok ? (p.a1_rows != nullptr ? static_cast<int64_t>(p.a1_rows[row]) : row) : 0) * p.ldr : nullptr;
     for (int cb = half; cb < n_blocks; cb += 2) {
       uint32_t r[16];
       tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(cb * 16), r);

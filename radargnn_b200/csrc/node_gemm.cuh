@@ -30,6 +30,7 @@ struct TcWeightBlocks {
 
 struct TcGemmParams {
   const float* a1 = nullptr; int64_t lda1 = 0; int32_t k1 = 0;   // 16-byte aligned rows, k1 % 4 == 0
+  const int32_t* a1_rows = nullptr;                              // optional gather map for a1 / residual rows
   const float* a2 = nullptr; int64_t lda2 = 0; int32_t k2 = 0;   // optional, k2 % 4 == 0
   int32_t k3 = 0;                                                // 0, or k1: third segment rowscale * a1
   const int32_t* csc_ptr = nullptr; int32_t rowscale_mode = 0;   // 1: in-degree > 0, 2: in-degree

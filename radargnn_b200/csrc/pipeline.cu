@@ -141,7 +141,8 @@ int rgnn_pipeline_forward(const rgnn_pipeline_desc* desc, const float* pos, cons
     if (expect != n_edges) return RGNN_ERR_INVALID_ARGUMENT;
     RGNN_RETURN_IF_ERROR(build_cell_lists(basis, RGNN_F32, desc->distance_dims, frame_ptr_host, n_frames, desc->k, w.graph, stream));
     RGNN_CUDA_CHECK(cudaMemsetAsync(w.csc.count, 0, sizeof(int32_t) * (n + 1), stream));
-    RGNN_RETURN_IF_ERROR(knn_query(RGNN_F32, desc->distance_dims, n, desc->k, edge_index, n_edges, w.csc.count, w.graph, stream));
+    RGNN_RETURN_IF_ERROR(knn_query(RGNN_F32, desc->distance_dims, n, desc->k, edge_index, n_edges, w.csc.count,
+                                   w.graph.rank, w.graph, stream));
     counts_ready = true;
   } else {
     // radius: the edge count is data dependent; the caller learned it from
@@ -164,12 +165,16 @@ int rgnn_pipeline_forward(const rgnn_pipeline_desc* desc, const float* pos, cons
   bool ordered = false;
   for (int l = 0; l < desc->n_layers; ++l)
     if (desc->layers[l].aggr == RGNN_AGGR_ADD || desc->layers[l].aggr == RGNN_AGGR_MEAN) ordered = true;
-  RGNN_RETURN_IF_ERROR(csc_build(edge_index, n_edges, n, counts_ready, ordered, w.csc, w.csc_ptr, w.csc_src, w.csc_eid, stream));
+  // The conv stack runs in CELL-SORTED node order (node r = original point sorted_idx[r]): spatial
+  // neighbours are then neighbours in memory, so the per-edge gathers of B[source] hit L1 / L2.
+  RGNN_RETURN_IF_ERROR(csc_build(edge_index, n_edges, n, counts_ready, ordered, w.csc, w.csc_ptr, w.csc_src, w.csc_eid,
+                                 stream, w.graph.rank));
   RGNN_RETURN_IF_ERROR(gather_edge_rows(edge_attr, w.csc_eid, n_edges, de, w.ea_csc, stream));
 
   // ---- 4. conv -> BatchNorm(train) -> ReLU, L times ------------------------------------------
   ConvInput in;
   in.x = x0; in.ldx = desc->layers[0].in_channels;
+  in.rows = w.graph.sorted_idx;  // layer 0 gathers its input rows into sorted order
   for (int l = 0; l < desc->n_layers; ++l) {
     const rgnn_conv_desc& c = desc->layers[l];
     ConvShape s;
@@ -192,11 +197,12 @@ int rgnn_pipeline_forward(const rgnn_pipeline_desc* desc, const float* pos, cons
       RGNN_RETURN_IF_ERROR(bn_statistics(out, s.c_out, n, s.c_out, bw, bb, desc->bn_eps, 0.f, nullptr, nullptr,
                                          st, st + c_max, st + 2 * c_max, w.bn_scratch, stream));
     }
-    in.x = out; in.ldx = s.c_out;
+    in.x = out; in.ldx = s.c_out; in.rows = nullptr;
     in.mean = st; in.scale = st + c_max; in.beta = st + 2 * c_max; in.relu = 1;
   }
   const int32_t c_last = desc->layers[desc->n_layers - 1].out_channels;
-  return bn_apply(in.x, in.ldx, n, c_last, in.mean, in.scale, in.beta, 1, h, c_last, stream);
+  // last BatchNorm + ReLU, scattered back to the caller's node order
+  return bn_apply(in.x, in.ldx, n, c_last, in.mean, in.scale, in.beta, 1, h, c_last, stream, w.graph.sorted_idx);
 }
 
 size_t rgnn_pipeline_host_workspace_bytes(const rgnn_pipeline_desc* desc, int64_t n_points, int32_t n_frames,
