@@ -358,14 +358,14 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
     const int64_t ldpost = s.c + s.p;
     wb.count = 2;
     wb.block[0] = {d.post_weight[0], ldpost, s.c_out, s.c, 0, 0};
-    wb.block[1] = {d.post_weight[0] + s.c, ldpost, s.c_out, s.p, s.c, 0};
+    wb.block[1] = {d.post_weight[0] + s.c, ldpost, s.c_out, s.p, tc_seg_pad(s.c), 0};  // segments start on 32-float chunks
     const bool third_segment = mpnn && d.aggr == RGNN_AGGR_ADD;
     if (mpnn) {
       RGNN_RETURN_IF_ERROR(tc_fold_weights(d.post_weight[0] + s.c, ldpost, d.pre_weight[0], s.p, s.c_out, s.p, s.c,
                                            w.w_fold, stream));
       wb.count = 3;
       if (third_segment) {
-        wb.block[2] = {w.w_fold, s.c, s.c_out, s.c, s.c + s.pp, 0};   // deg * x segment
+        wb.block[2] = {w.w_fold, s.c, s.c_out, s.c, tc_seg_pad(s.c) + tc_seg_pad(s.pp), 0};   // deg * x segment
       } else {
         wb.block[2] = {w.w_fold, s.c, s.c_out, s.c, 0, 1};            // added onto W_x: (W_x + W_m W_t) x
       }

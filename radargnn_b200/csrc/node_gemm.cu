@@ -68,6 +68,29 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       : "memory");
 }
 
+// warp-uniform variants: every lane executes the surrounding code, `leader` selects the issuing lane
+__device__ __forceinline__ void umma_tf32_pred(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(leader)
+      : "memory");
+}
+
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -145,20 +168,31 @@ fold_weights_kernel(const float* __restrict__ w_m, int64_t ld_m, const float* __
 }
 
 // ---- the GEMM ------------------------------------------------------------------------------
-constexpr int kRing = 2;  // raw K-chunk slots (cp.async targets), 16 KB each
+// Warp roles (416 threads, one CTA per SM, persistent over 128-row tiles):
+//   warps 0-7   producers: cp.async raw K chunks, transform + hi/lo split, write the swizzled A stages
+//   warps 8-11  epilogue:  TMEM -> registers -> global (+ BatchNorm column sums), one TMEM lane quarter each
+//   warp  12    MMA issuer (one lane): tcgen05.mma per 8-float k-step, tcgen05.commit to the barriers
+// Hand-offs are mbarriers only: full[s] (producers -> MMA), empty[s] (MMA done -> producers),
+// acc_full[a] (MMA -> epilogue), acc_empty[a] (epilogue -> MMA).  Two A stages and two TMEM
+// accumulators, so loads, conversion, MMAs and the epilogue of consecutive tiles overlap.
+constexpr int kRing = 2;             // raw K-chunk slots (cp.async targets), 16 KB each
+constexpr int kProducerThreads = 256;
+constexpr int kEpilogueThreads = 128;
+constexpr int kGemmThreads = kProducerThreads + kEpilogueThreads + 32;
 
 struct SmemLayout {
   float* w_hi; float* w_lo;
   float* a_hi[2]; float* a_lo[2];  // converted chunks (hi / lo images), 1 or 2 stages
-  float* raw;                 // [kRing][128 x 32] chunks as loaded (same swizzled layout)
-  float* col_sum;             // [4][np]
-  float* col_sq;              // [4][np]
-  float* bias;                // [np]
-  uint64_t* bar;              // [2] one per A stage
+  float* raw;                      // [kRing][128 x 32] chunks as loaded (same swizzled layout)
+  float* col_sum;                  // [2 accumulators][4 quarters][np]
+  float* col_sq;
+  float* bias;                     // [np]
+  float* bn;                       // [3][k1] mean | scale | beta of the a1 transform
+  uint64_t* bar;                   // full[2], empty[2], acc_full[2], acc_empty[2]
   uint32_t* tmem_base;
 };
 
-__device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int np, int kp32, int a_stages) {
+__device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int np, int kp32, int a_stages, int k1) {
   SmemLayout s;
   float* f = reinterpret_cast<float*>(base);
   s.w_hi = f; f += static_cast<size_t>(np) * kp32;
@@ -171,10 +205,11 @@ __device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int np, in
     s.a_lo[1] = f; f += kABufFloats;
   }
   s.raw = f; f += kRing * kABufFloats;
-  s.col_sum = f; f += 4 * np;
-  s.col_sq = f; f += 4 * np;
+  s.col_sum = f; f += 8 * np;
+  s.col_sq = f; f += 8 * np;
   s.bias = f; f += np;
-  s.bar = reinterpret_cast<uint64_t*>(f); f += 4;
+  s.bn = f; f += 3 * k1;
+  s.bar = reinterpret_cast<uint64_t*>(f); f += 16;
   s.tmem_base = reinterpret_cast<uint32_t*>(f);
   return s;
 }
@@ -183,280 +218,332 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
 node_gemm_kernel(TcGemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int np = p.np, kp = p.kp, kp32 = (p.kp + 31) & ~31;
   const int a_stages = p.a_stages;
-  const SmemLayout s = carve_smem(smem_raw, np, kp32, a_stages);
+  const SmemLayout s = carve_smem(smem_raw, np, kp32, a_stages, p.k1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tmem_cols = np <= 32 ? 32 : (np <= 64 ? 64 : (np <= 128 ? 128 : 256));
+  const int acc_cols = 2 * np;
+  const int tmem_cols = acc_cols <= 32 ? 32 : (acc_cols <= 64 ? 64 : (acc_cols <= 128 ? 128 : (acc_cols <= 256 ? 256 : 512)));
+  uint64_t* full = s.bar;           // [2]
+  uint64_t* empty = s.bar + 2;      // [2]
+  uint64_t* acc_full = s.bar + 4;   // [2]
+  uint64_t* acc_empty = s.bar + 6;  // [2]
 
-  // ---- one-time setup: barrier, TMEM, resident weights, bias ----------------------------------
+  // ---- one-time setup: barriers, TMEM, resident weights, bias, BatchNorm-on-load parameters ------
   if (tid == 0) {
-    mbar_init(&s.bar[0], 1);
-    mbar_init(&s.bar[1], 1);
+    mbar_init(&full[0], kProducerThreads); mbar_init(&full[1], kProducerThreads);
+    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], kEpilogueThreads); mbar_init(&acc_empty[1], kEpilogueThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s.tmem_base)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-
-  // chunk stream of this CTA: chunk g = (tile index g / chunks_per_tile, K offset (g % chunks_per_tile) * 32)
-  const int chunks_per_tile = (kp + kKc - 1) / kKc;
-  const int64_t n_tiles = (p.m + kRows - 1) / kRows;
-  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t my_chunks = my_tiles * chunks_per_tile;
-  const int k_total = p.k1 + p.k2 + p.k3;
-  const int r8 = lane & 7, kq = lane >> 3;
-  const uint32_t raw_addr = smem_u32(s.raw);
-
-  // issue the cp.async loads of this thread's 4 items of chunk g (zero-filled outside the matrix)
-  auto prefetch = [&](int64_t g) {
-    if (g < my_chunks) {
-      const int64_t tile = blockIdx.x + (g / chunks_per_tile) * gridDim.x;
-      const int k0 = static_cast<int>(g % chunks_per_tile) * kKc;
-      const int slot = static_cast<int>(g % kRing);
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int u = it * 8 + warp;
-        const int rb = u >> 1, k4 = ((u & 1) << 2) + kq;
-        const int64_t row = tile * kRows + rb * 8 + r8;
-        const int kg = k0 + k4 * 4;
-        const float* src = p.a1;
-        uint32_t bytes = 0;
-        if (row < p.m && kg < k_total) {
-          bytes = 16;
-          if (kg >= p.k1 && kg < p.k1 + p.k2) {
-            src = p.a2 + row * p.lda2 + (kg - p.k1);
-          } else {
-            const int64_t arow = p.a1_rows != nullptr ? p.a1_rows[row] : row;
-            src = p.a1 + arow * p.lda1 + (kg < p.k1 ? kg : kg - p.k1 - p.k2);
-          }
-        }
-        cp_async16(raw_addr + static_cast<uint32_t>(slot * kABufFloats + rb * 256 + r8 * 32 + ((k4 ^ r8) << 2)) * 4u, src, bytes);
+  {
+    // resident weights: fire-and-forget cp.async (no register staging), waited for before the barrier
+    const int total16 = (2 * np * kp32) >> 2;
+    const uint32_t w_addr = smem_u32(s.w_hi);
+    for (int i = tid; i < total16; i += kGemmThreads) cp_async16(w_addr + i * 16u, p.wpack + i * 4, 16);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int i = tid; i < np; i += kGemmThreads) s.bias[i] = (p.bias != nullptr && i < p.n) ? p.bias[i] : 0.f;
+    if (p.a1_mean != nullptr) {
+      for (int i = tid; i < p.k1; i += kGemmThreads) {
+        s.bn[i] = p.a1_mean[i]; s.bn[p.k1 + i] = p.a1_scale[i]; s.bn[2 * p.k1 + i] = p.a1_beta[i];
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");  // always commit: uniform group accounting
-  };
-  prefetch(0);
-  prefetch(1);
-
-  {
-    const float4* src = reinterpret_cast<const float4*>(p.wpack);
-    float4* dst = reinterpret_cast<float4*>(s.w_hi);
-    const int total4 = (2 * np * kp32) >> 2;
-    for (int i = tid; i < total4; i += kThreads) dst[i] = src[i];
-    for (int i = tid; i < np; i += kThreads) s.bias[i] = (p.bias != nullptr && i < p.n) ? p.bias[i] : 0.f;
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *s.tmem_base;
-  const uint32_t idesc = umma_idesc_tf32(kRows, np);
-  const uint32_t w_hi_addr = smem_u32(s.w_hi), w_lo_addr = smem_u32(s.w_lo);
-  const uint32_t w_panel_bytes = static_cast<uint32_t>(np) * 128u;  // one 32-float K block of W
-  const uint32_t a_hi_addr0 = smem_u32(s.a_hi[0]), a_lo_addr0 = smem_u32(s.a_lo[0]);
-  const uint32_t a_hi_addr1 = smem_u32(s.a_hi[1]), a_lo_addr1 = smem_u32(s.a_lo[1]);
 
-  // per A stage: parity of the next completion to wait for, and whether a commit is outstanding
-  uint32_t phase0 = 0u, phase1 = 0u;
-  bool pending0 = false, pending1 = false;
+  const int chunks_per_tile = (kp + kKc - 1) / kKc;
+  const int64_t n_tiles = (p.m + kRows - 1) / kRows;
+  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   bool timed_out = false;
-  int64_t g = 0;
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * kRows;
-    for (int k0 = 0; k0 < kp; k0 += kKc, ++g) {
-      asm volatile("cp.async.wait_group 1;" ::: "memory");  // this thread's items of chunk g have landed
-      const float* raw = s.raw + (g & 1) * kABufFloats;
-      // ---- transform (BatchNorm + ReLU on load, row scale) and hi / lo split, in registers --------
-      float4 hi[4], lo[4];
+  if (warp < 8) {
+    // =========================== producers ===========================
+    // K is laid out segment by segment, each padded to whole 32-float chunks, so a chunk lies in
+    // exactly one segment: the segment logic is decided once per chunk, not per element.
+    const int k1p = (p.k1 + 31) & ~31, k2p = (p.k2 + 31) & ~31;
+    const int r8 = lane & 7, kq = lane >> 3;
+    const uint32_t raw_addr = smem_u32(s.raw);
+    const bool has_bn = p.a1_mean != nullptr;
+    const int m32 = static_cast<int>(p.m);
+    // chunk-invariant coordinates of this thread's 4 items
+    int rloc[4], kcol[4], off[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int u = it * 8 + warp;
+      const int k4 = ((u & 1) << 2) + kq;
+      rloc[it] = (u >> 1) * 8 + r8;
+      kcol[it] = k4 * 4;
+      off[it] = (u >> 1) * 256 + r8 * 32 + ((k4 ^ r8) << 2);
+    }
+    // ---- prefetch stream (runs up to two chunks ahead, possibly already in the next tile) --------
+    int64_t pf_tl = 0;
+    int pf_kc = 0, pf_slot = 0;
+    const float* pf_a1[4];
+    const float* pf_a2[4];
+    bool pf_ok[4];
+    auto prefetch = [&]() {
+      if (pf_tl < my_tiles) {
+        if (pf_kc == 0) {
+          const int row0 = static_cast<int>(blockIdx.x + pf_tl * gridDim.x) * kRows;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int row = row0 + rloc[it];
+            pf_ok[it] = row < m32;
+            const int rr = pf_ok[it] ? row : 0;
+            const int64_t arow = p.a1_rows != nullptr ? p.a1_rows[rr] : rr;
+            pf_a1[it] = p.a1 + arow * p.lda1 + kcol[it];
+            pf_a2[it] = p.a2 != nullptr ? p.a2 + static_cast<int64_t>(rr) * p.lda2 + kcol[it] : p.a1;
+          }
+        }
+        const int k0 = pf_kc * kKc;
+        const uint32_t slot_addr = raw_addr + static_cast<uint32_t>(pf_slot) * (kABufFloats * 4u);
+        const bool seg1 = k0 >= k1p && k0 < k1p + k2p;
+        const int col0 = k0 < k1p ? k0 : (seg1 ? k0 - k1p : k0 - k1p - k2p);
+        const int seg_len = seg1 ? p.k2 : p.k1;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const bool valid = pf_ok[it] && (col0 + kcol[it] < seg_len);
+          const float* src = (seg1 ? pf_a2[it] : pf_a1[it]) + col0;
+          cp_async16(slot_addr + off[it] * 4u, valid ? src : p.a1, valid ? 16u : 0u);
+        }
+        if (++pf_kc == chunks_per_tile) { pf_kc = 0; ++pf_tl; }
+        pf_slot ^= 1;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");  // always commit: uniform group accounting
+    };
+    prefetch();
+    prefetch();
+    uint32_t g = 0;  // chunk counter of the convert stream
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      const int row0 = static_cast<int>(blockIdx.x + tl * gridDim.x) * kRows;
+      bool ok[4];
+      float rs[4];
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const int u = it * 8 + warp;
-        const int rb = u >> 1, k4 = ((u & 1) << 2) + kq;
-        const int64_t row = row0 + rb * 8 + r8;
-        const int kg = k0 + k4 * 4;
-        float4 v = *reinterpret_cast<const float4*>(raw + rb * 256 + r8 * 32 + ((k4 ^ r8) << 2));
-        if (row < p.m && kg < k_total) {
-          if (kg < p.k1 || kg >= p.k1 + p.k2) {
-            const int c = kg < p.k1 ? kg : kg - p.k1 - p.k2;
-            if (p.a1_mean != nullptr) {
-              const float4 mu = *reinterpret_cast<const float4*>(p.a1_mean + c);
-              const float4 sc = *reinterpret_cast<const float4*>(p.a1_scale + c);
-              const float4 be = *reinterpret_cast<const float4*>(p.a1_beta + c);
+        const int row = row0 + rloc[it];
+        ok[it] = row < m32;
+        rs[it] = 1.f;
+        if (p.k3 > 0 && ok[it]) {
+          const int deg = p.csc_ptr[row + 1] - p.csc_ptr[row];
+          rs[it] = p.rowscale_mode == 2 ? static_cast<float>(deg) : (deg > 0 ? 1.f : 0.f);
+        }
+      }
+      for (int kc = 0; kc < chunks_per_tile; ++kc, ++g) {
+        const int k0 = kc * kKc;
+        const bool seg1 = k0 >= k1p && k0 < k1p + k2p;
+        const bool seg2 = k0 >= k1p + k2p;
+        const int col0 = k0 < k1p ? k0 : (seg1 ? k0 - k1p : k0 - k1p - k2p);
+        const int seg_len = seg1 ? p.k2 : p.k1;
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // this thread's items of chunk g have landed
+        const float* raw = s.raw + (g & 1u) * kABufFloats;
+        float4 hi[4], lo[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          float4 v = *reinterpret_cast<const float4*>(raw + off[it]);
+          const int c = col0 + kcol[it];
+          const bool valid = ok[it] && c < seg_len;
+          if (!seg1) {
+            if (has_bn) {
+              const float4 mu = *reinterpret_cast<const float4*>(s.bn + c);
+              const float4 sc = *reinterpret_cast<const float4*>(s.bn + p.k1 + c);
+              const float4 be = *reinterpret_cast<const float4*>(s.bn + 2 * p.k1 + c);
               v.x = (v.x - mu.x) * sc.x + be.x; v.y = (v.y - mu.y) * sc.y + be.y;
               v.z = (v.z - mu.z) * sc.z + be.z; v.w = (v.w - mu.w) * sc.w + be.w;
             }
             if (p.relu_a1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            if (kg >= p.k1) {  // third segment: rowscale * a1 (in-degree flag or in-degree)
-              const int deg = p.csc_ptr[row + 1] - p.csc_ptr[row];
-              const float rs = p.rowscale_mode == 2 ? static_cast<float>(deg) : (deg > 0 ? 1.f : 0.f);
-              v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
-            }
+            if (seg2) { v.x *= rs[it]; v.y *= rs[it]; v.z *= rs[it]; v.w *= rs[it]; }
           } else if (p.relu_a2) {
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
           }
+          if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+          split_tf32(v.x, hi[it].x, lo[it].x); split_tf32(v.y, hi[it].y, lo[it].y);
+          split_tf32(v.z, hi[it].z, lo[it].z); split_tf32(v.w, hi[it].w, lo[it].w);
         }
-        split_tf32(v.x, hi[it].x, lo[it].x); split_tf32(v.y, hi[it].y, lo[it].y);
-        split_tf32(v.z, hi[it].z, lo[it].z); split_tf32(v.w, hi[it].w, lo[it].w);
-      }
-      // this thread's raw items are in registers: its slot can take chunk g + 2 right away
-      prefetch(g + 2);
-      // the A stage being overwritten must have been drained by the MMAs that read it
-      const int b = a_stages == 2 ? static_cast<int>(g & 1) : 0;
-      if (b == 0) {
-        if (pending0) { if (!mbar_wait(&s.bar[0], phase0)) timed_out = true; phase0 ^= 1u; pending0 = false; }
-      } else {
-        if (pending1) { if (!mbar_wait(&s.bar[1], phase1)) timed_out = true; phase1 ^= 1u; pending1 = false; }
-      }
-      float* dst_hi = b == 0 ? s.a_hi[0] : s.a_hi[1];
-      float* dst_lo = b == 0 ? s.a_lo[0] : s.a_lo[1];
+        prefetch();  // the raw items are in registers: the slot can take chunk g + 2 right away
+        // wait until the MMAs of the previous use of this A stage have drained it
+        const uint32_t b = a_stages == 2 ? (g & 1u) : 0u;
+        const uint32_t use = a_stages == 2 ? (g >> 1) : g;
+        if (use >= 1u && !mbar_wait(&empty[b], (use - 1u) & 1u)) timed_out = true;
+        float* dst_hi = s.a_hi[b];
+        float* dst_lo = s.a_lo[b];
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int u = it * 8 + warp;
-        const int off = (u >> 1) * 256 + r8 * 32 + (((((u & 1) << 2) + kq) ^ r8) << 2);
-        *reinterpret_cast<float4*>(dst_hi + off) = hi[it];
-        *reinterpret_cast<float4*>(dst_lo + off) = lo[it];
+        for (int it = 0; it < 4; ++it) {
+          *reinterpret_cast<float4*>(dst_hi + off[it]) = hi[it];
+          *reinterpret_cast<float4*>(dst_lo + off[it]) = lo[it];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (MMA)
+        mbar_arrive(&full[b]);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (MMA)
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      // ---- one thread issues the MMAs of this chunk; they run while the next chunks are converted ---
-      if (tid == 0) {
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp == 12) {
+    // =========================== MMA issuer ===========================
+    // The whole warp runs this loop with uniform control flow and uniform operands (descriptors stay
+    // in uniform registers, advancing one is a 32-bit add on its low word); only the tcgen05
+    // instructions themselves are predicated to lane 0.  Twelve MMAs per chunk, fully unrolled.
+    const uint32_t leader = lane == 0 ? 1u : 0u;
+    const uint32_t idesc = umma_idesc_tf32(kRows, np);
+    const uint32_t w_panel16 = (static_cast<uint32_t>(np) * 128u) >> 4;  // one 32-float K block of W, in 16-byte units
+    const uint64_t dw_hi0 = umma_desc(smem_u32(s.w_hi)), dw_lo0 = umma_desc(smem_u32(s.w_lo));
+    const uint64_t da_hi0[2] = {umma_desc(smem_u32(s.a_hi[0])), umma_desc(smem_u32(s.a_hi[1]))};
+    const uint64_t da_lo0[2] = {umma_desc(smem_u32(s.a_lo[0])), umma_desc(smem_u32(s.a_lo[1]))};
+    uint32_t g = 0;
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      const int ab = static_cast<int>(tl & 1);
+      if (tl >= 2 && !mbar_wait(&acc_empty[ab], static_cast<uint32_t>(((tl >> 1) - 1) & 1))) timed_out = true;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_addr = tmem_d + static_cast<uint32_t>(ab * np);
+      for (int kc = 0; kc < chunks_per_tile; ++kc, ++g) {
+        const uint32_t b = a_stages == 2 ? (g & 1u) : 0u;
+        const uint32_t use = a_stages == 2 ? (g >> 1) : g;
+        if (!mbar_wait(&full[b], use & 1u)) timed_out = true;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int steps = (kp - k0 < kKc ? kp - k0 : kKc) >> 3;
-        const uint32_t a_hi_addr = b == 0 ? a_hi_addr0 : a_hi_addr1, a_lo_addr = b == 0 ? a_lo_addr0 : a_lo_addr1;
-        for (int jj = 0; jj < steps; ++jj) {
-          const int j = (k0 >> 3) + jj;
-          const uint32_t w_off = static_cast<uint32_t>(j >> 2) * w_panel_bytes + static_cast<uint32_t>(j & 3) * 32u;
-          const uint64_t da_hi = umma_desc(a_hi_addr + jj * 32);
-          const uint64_t da_lo = umma_desc(a_lo_addr + jj * 32);
-          const uint64_t dw_hi = umma_desc(w_hi_addr + w_off);
-          const uint64_t dw_lo = umma_desc(w_lo_addr + w_off);
-          umma_tf32(tmem_d, da_hi, dw_hi, idesc, j > 0 ? 1u : 0u);
-          umma_tf32(tmem_d, da_lo, dw_hi, idesc, 1u);
-          umma_tf32(tmem_d, da_hi, dw_lo, idesc, 1u);
-        }
-        umma_commit(b == 0 ? &s.bar[0] : &s.bar[1]);
-      }
-      if (b == 0) pending0 = true; else pending1 = true;
-    }
-    // ---- accumulator complete: the last commit covers every earlier MMA of the tile ---------------
-    {
-      const int b = a_stages == 2 ? static_cast<int>((g - 1) & 1) : 0;
-      if (b == 0) { if (!mbar_wait(&s.bar[0], phase0)) timed_out = true; phase0 ^= 1u; pending0 = false; }
-      else { if (!mbar_wait(&s.bar[1], phase1)) timed_out = true; phase1 ^= 1u; pending1 = false; }
-    }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // ---- epilogue: TMEM -> registers (thread = row, 16 columns) -> bias / residual -> global ----
-    // Each lane stores 4 x 16 bytes of its own row; the column sums for BatchNorm come from a
-    // fixed-order butterfly over the 32 rows of the warp.
-    const int q = warp & 3, half = warp >> 2;
-    const int n_blocks = np >> 4;
-    const int64_t row = row0 + q * 32 + lane;
-    const bool row_ok = row < p.m;
-    const bool vec = ((p.ldy & 3) == 0) && ((p.n_store & 3) == 0) && (p.residual == nullptr || (p.ldr & 3) == 0);
-    float* yrow = p.y + (row_ok ? row : 0) * p.ldy;
-    const float* rrow = p.residual != nullptr
-        ? p.residual + (row_ok ? (p.a1_rows != nullptr ? static_cast<int64_t>(p.a1_rows[row]) : row) : 0) * p.ldr : nullptr;
-    for (int cb = half; cb < n_blocks; cb += 2) {
-      uint32_t r[16];
-      tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(cb * 16), r);
-      float v[16];
+        const uint64_t a_hi = b == 0 ? da_hi0[0] : da_hi0[1];
+        const uint64_t a_lo = b == 0 ? da_lo0[0] : da_lo0[1];
+        const uint64_t w_hi = dw_hi0 + static_cast<uint64_t>(static_cast<uint32_t>(kc) * w_panel16);
+        const uint64_t w_lo = dw_lo0 + static_cast<uint64_t>(static_cast<uint32_t>(kc) * w_panel16);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = cb * 16 + j;
-        v[j] = col < p.n ? __uint_as_float(r[j]) + s.bias[col] : 0.f;
+        for (int jj = 0; jj < 4; ++jj) {  // a k-step is 32 bytes = 2 descriptor units further into the panel
+          umma_tf32_pred(d_addr, a_hi + 2 * jj, w_hi + 2 * jj, idesc, (kc > 0 || jj > 0) ? 1u : 0u, leader);
+          umma_tf32_pred(d_addr, a_lo + 2 * jj, w_hi + 2 * jj, idesc, 1u, leader);
+          umma_tf32_pred(d_addr, a_hi + 2 * jj, w_lo + 2 * jj, idesc, 1u, leader);
+        }
+        umma_commit_pred(&empty[b], leader);   // arrives when the MMAs above have finished reading the stage
       }
-      if (rrow != nullptr && row_ok) {
+      umma_commit_pred(&acc_full[ab], leader);  // ... and when the whole tile's accumulator is complete
+    }
+  } else {
+    // =========================== epilogue ===========================
+    // thread = row (TMEM lane), 16 columns per tcgen05.ld; each lane stores 4 x 16 bytes of its own
+    // row; BatchNorm column sums via a fixed-order butterfly over the warp's 32 rows.
+    const int q = warp - 8;
+    const int n_blocks = np >> 4;
+    const bool vec = ((p.ldy & 3) == 0) && ((p.n_store & 3) == 0);
+    const int et = tid - kProducerThreads;  // 0..127
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      const int ab = static_cast<int>(tl & 1);
+      const int64_t tile = blockIdx.x + tl * gridDim.x;
+      const int64_t row = tile * kRows + q * 32 + lane;
+      const bool row_ok = row < p.m;
+      float* yrow = p.y + (row_ok ? row : 0) * p.ldy;
+      const float* rrow = p.residual != nullptr
+          ? p.residual + (row_ok ? (p.a1_rows != nullptr ? static_cast<int64_t>(p.a1_rows[row]) : row) : 0) * p.ldr : nullptr;
+      if (!mbar_wait(&acc_full[ab], static_cast<uint32_t>((tl >> 1) & 1))) timed_out = true;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float* csum = s.col_sum + (ab * 4 + q) * np;
+      float* csq = s.col_sq + (ab * 4 + q) * np;
+      for (int cb = 0; cb < n_blocks; ++cb) {
+        uint32_t r[16];
+        tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ab * np + cb * 16), r);
+        float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int col = cb * 16 + j;
-          if (col < p.n) {
-            float rv = rrow[col];
-            if (p.res_mean != nullptr) rv = (rv - p.res_mean[col]) * p.res_scale[col] + p.res_beta[col];
-            if (p.res_relu) rv = fmaxf(rv, 0.f);
-            v[j] += rv;
-          }
+          v[j] = col < p.n ? __uint_as_float(r[j]) + s.bias[col] : 0.f;
         }
-      }
-      if (row_ok) {
-        if (vec) {
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const int col = cb * 16 + j4 * 4;
-            if (col < p.n_store) *reinterpret_cast<float4*>(yrow + col) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-          }
-        } else {
+        if (rrow != nullptr && row_ok) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = cb * 16 + j;
-            if (col < p.n_store) yrow[col] = v[j];
+            if (col < p.n) {
+              float rv = rrow[col];
+              if (p.res_mean != nullptr) rv = (rv - p.res_mean[col]) * p.res_scale[col] + p.res_beta[col];
+              if (p.res_relu) rv = fmaxf(rv, 0.f);
+              v[j] += rv;
+            }
+          }
+        }
+        if (row_ok) {
+          if (vec) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const int col = cb * 16 + j4 * 4;
+              if (col < p.n_store) *reinterpret_cast<float4*>(yrow + col) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = cb * 16 + j;
+              if (col < p.n_store) yrow[col] = v[j];
+            }
+          }
+        }
+        if (p.bn_partial != nullptr) {
+          float sv[16], sq[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { sv[j] = row_ok ? v[j] : 0.f; sq[j] = sv[j] * sv[j]; }
+#pragma unroll
+          for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+            // lanes with `bit` clear keep columns [0, w), the others keep [w, 2w)
+            const bool upper = (lane & bit) != 0;
+#pragma unroll
+            for (int j = 0; j < w; ++j) {
+              const float send_s = upper ? sv[j] : sv[j + w], keep_s = upper ? sv[j + w] : sv[j];
+              const float send_q = upper ? sq[j] : sq[j + w], keep_q = upper ? sq[j + w] : sq[j];
+              sv[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+              sq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+            }
+          }
+          sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+          sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
+          if ((lane & 1) == 0) {
+            const int col = cb * 16 + (((lane >> 4) & 1) << 3 | ((lane >> 3) & 1) << 2 | ((lane >> 2) & 1) << 1 | ((lane >> 1) & 1));
+            csum[col] = sv[0];
+            csq[col] = sq[0];
           }
         }
       }
+      // accumulator drained: hand it back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&acc_empty[ab]);
       if (p.bn_partial != nullptr) {
-        // column sums over the warp's 32 rows: butterfly that halves the columns a lane carries
-        float sv[16], sq[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { sv[j] = row_ok ? v[j] : 0.f; sq[j] = sv[j] * sv[j]; }
-#pragma unroll
-        for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
-          // lanes with `bit` clear keep columns [0, w), the others keep [w, 2w)
-          const bool upper = (lane & bit) != 0;
-#pragma unroll
-          for (int j = 0; j < w; ++j) {
-            const float send_s = upper ? sv[j] : sv[j + w], keep_s = upper ? sv[j + w] : sv[j];
-            const float send_q = upper ? sq[j] : sq[j + w], keep_q = upper ? sq[j + w] : sq[j];
-            sv[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
-            sq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
-          }
-        }
-        // lane now holds column cb*16 + (lane >> 1) summed over half the rows (lane parity): finish
-        sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
-        sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
-        if ((lane & 1) == 0) {
-          const int col = cb * 16 + (((lane >> 4) & 1) << 3 | ((lane >> 3) & 1) << 2 | ((lane >> 2) & 1) << 1 | ((lane >> 1) & 1));
-          s.col_sum[q * np + col] = sv[0];
-          s.col_sq[q * np + col] = sq[0];
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four quarters' column sums are in shared memory
+        const float* cs = s.col_sum + ab * 4 * np;
+        const float* cq = s.col_sq + ab * 4 * np;
+        for (int c = et; c < p.n; c += kEpilogueThreads) {
+          const double sum = (static_cast<double>(cs[c]) + static_cast<double>(cs[np + c])) +
+                             (static_cast<double>(cs[2 * np + c]) + static_cast<double>(cs[3 * np + c]));
+          const double sq2 = (static_cast<double>(cq[c]) + static_cast<double>(cq[np + c])) +
+                             (static_cast<double>(cq[2 * np + c]) + static_cast<double>(cq[3 * np + c]));
+          p.bn_partial[(tile * 2) * p.n + c] = sum;
+          p.bn_partial[(tile * 2 + 1) * p.n + c] = sq2;
         }
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();  // TMEM drained (the next tile's first MMA overwrites it), column sums complete
-    if (p.bn_partial != nullptr) {
-      for (int c = tid; c < p.n; c += kThreads) {
-        const double sum = (static_cast<double>(s.col_sum[c]) + static_cast<double>(s.col_sum[np + c])) +
-                           (static_cast<double>(s.col_sum[2 * np + c]) + static_cast<double>(s.col_sum[3 * np + c]));
-        const double sq = (static_cast<double>(s.col_sq[c]) + static_cast<double>(s.col_sq[np + c])) +
-                          (static_cast<double>(s.col_sq[2 * np + c]) + static_cast<double>(s.col_sq[3 * np + c]));
-        p.bn_partial[(tile * 2) * p.n + c] = sum;
-        p.bn_partial[(tile * 2 + 1) * p.n + c] = sq;
-      }
-    }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
-  asm volatile("cp.async.wait_all;" ::: "memory");
 
   if (timed_out && p.status != nullptr) atomicExch(p.status, RGNN_ERR_CUDA);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 12) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
   }
 }
 
 size_t smem_bytes_for(int np, int kp, int a_stages) {
   const size_t kp32 = (static_cast<size_t>(kp) + 31) & ~static_cast<size_t>(31);
-  return sizeof(float) * (2 * np * kp32 + (2 * a_stages + kRing) * kABufFloats + 8 * np + np + 4 + 4) + 64;
+  return sizeof(float) * (2 * np * kp32 + (2 * a_stages + kRing) * kABufFloats + 16 * np + np + 3 * kp32 + 32 + 4) + 64;
 }
 
 int pick_a_stages(int np, int kp) {
+  if (2 * np > 512) return 0;  // two TMEM accumulators
   if (smem_bytes_for(np, kp, 2) <= 227 * 1024) return 2;
   if (smem_bytes_for(np, kp, 1) <= 227 * 1024) return 1;
   return 0;
@@ -472,13 +559,13 @@ bool tc_gemm_supported(const TcGemmShape& sh) {
   }
   if (!enabled) return false;
   if (sh.k1 < 4 || sh.k1 % 4 != 0 || sh.k2 % 4 != 0 || sh.n < 1) return false;
-  const int np = tc_padded_n(sh.n), kp = tc_padded_k(sh.k1 + sh.k2 + sh.k3);
+  const int np = tc_padded_n(sh.n), kp = tc_padded_k(sh.k1, sh.k2, sh.k3);
   if (np > 256) return false;
   return pick_a_stages(np, kp) > 0;
 }
 
 size_t tc_pack_floats(const TcGemmShape& sh) {
-  return 2 * static_cast<size_t>(tc_padded_n(sh.n)) * ((tc_padded_k(sh.k1 + sh.k2 + sh.k3) + 31) & ~31);
+  return 2 * static_cast<size_t>(tc_padded_n(sh.n)) * tc_padded_k(sh.k1, sh.k2, sh.k3);
 }
 
 int tc_fold_weights(const float* w_m, int64_t ld_m, const float* w_t, int64_t ld_t, int c_out, int p, int c,
@@ -490,7 +577,7 @@ int tc_fold_weights(const float* w_m, int64_t ld_m, const float* w_t, int64_t ld
 }
 
 int tc_pack_weights(const TcWeightBlocks& blocks, const TcGemmShape& sh, float* wpack, cudaStream_t stream) {
-  const int np = tc_padded_n(sh.n), kp = (tc_padded_k(sh.k1 + sh.k2 + sh.k3) + 31) & ~31;
+  const int np = tc_padded_n(sh.n), kp = tc_padded_k(sh.k1, sh.k2, sh.k3);
   RGNN_PROFILE("weight_prep", stream);
   pack_weights_kernel<<<div_up(np * kp, 256), 256, 0, stream>>>(blocks, np, kp, wpack);
   RGNN_LAUNCH_CHECK();
@@ -500,7 +587,7 @@ int tc_pack_weights(const TcWeightBlocks& blocks, const TcGemmShape& sh, float* 
 int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
   if (p.m <= 0) return RGNN_OK;
   p.np = tc_padded_n(p.n);
-  p.kp = tc_padded_k(p.k1 + p.k2 + p.k3);
+  p.kp = tc_padded_k(p.k1, p.k2, p.k3);
   if (p.n_store < p.n) p.n_store = p.n;
   p.a_stages = pick_a_stages(p.np, p.kp);
   if (p.a_stages == 0) return RGNN_ERR_UNSUPPORTED;
@@ -513,7 +600,7 @@ int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
   const int64_t tiles = (p.m + kRows - 1) / kRows;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   RGNN_PROFILE(tag, stream);
-  node_gemm_kernel<<<grid, kThreads, smem, stream>>>(p);
+  node_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(p);
   RGNN_LAUNCH_CHECK();
   return RGNN_OK;
 }

@@ -13,7 +13,9 @@ struct TcGemmShape {
 };
 
 inline int tc_padded_n(int n) { return (n + 15) & ~15; }
-inline int tc_padded_k(int k) { return (k + 7) & ~7; }
+// every K segment is padded to whole 32-float chunks (one 128-byte swizzled panel column)
+inline int tc_seg_pad(int k) { return (k + 31) & ~31; }
+inline int tc_padded_k(int k1, int k2, int k3) { return tc_seg_pad(k1) + tc_seg_pad(k2) + tc_seg_pad(k3); }
 
 // one block of source weights copied into the packed image: rows x cols of a row-major matrix
 // (row stride ld) placed at K offset k_offset
