@@ -102,15 +102,15 @@ def kernel_algorithmic_bytes(name: str, n: int, e: int, wl: dict):
     p = 2 * c + de
     pp = (p + 3) // 4 * 4
     table = {
-        # B rows (unique) + A rows + slot sources + slot edge attributes + row pointers + M rows
-        "edge_aggregate": 4 * n * pp + 4 * n * pp + 4 * e + 4 * de * e + 4 * (n + 1) + 4 * n * pp,
-        "linear_pre_node": 4 * n * c + 4 * n * pp,            # read x, write one of A / B
-        "linear_post": 4 * n * c + 4 * n * pp + 4 * n * c,    # read x and M, write h
+        # B rows (unique) + slot sources + slot edge attributes + row pointers + M rows
+        "edge_aggregate": 4 * n * pp + 4 * e + 4 * de * e + 4 * (n + 1) + 4 * n * pp,
+        "node_gemm_pre": 4 * n * c + 4 * n * pp,             # read x, write B = x W_s^T
+        "node_gemm_post": 4 * n * c + 4 * n * pp + 4 * n * c,  # read x and M, write h
+        "linear_pre_node": 4 * n * c + 4 * n * pp,
+        "linear_post": 4 * n * c + 4 * n * pp + 4 * n * c,
         "knn_query": 8 * n + 16 * n + 16 * e + 4 * n,        # sorted points + ids/cells + edge_index + in-degree
         "bn_statistics": 4 * n * c,
         "edge_features": 16 * e + 16 * n + 4 * de * e,
-        "fused_layer": 4 * n * c + 4 * n * pp + 4 * e + 4 * de * e + 4 * (n + 1) + 4 * n * c,
-        "node_gemm": 4 * n * c + 4 * n * pp,
     }
     return table.get(name)
 

@@ -20,6 +20,8 @@
 //     memory for all tiles of the CTA;
 //   * epilogue: tcgen05.ld (32 lanes x 16 columns per warp) -> bias / residual -> per-warp staging ->
 //     coalesced stores, plus deterministic per-tile column sums for the BatchNorm statistics.
+#include <string.h>
+
 #include "node_gemm.cuh"
 
 namespace rgnn {
@@ -168,17 +170,22 @@ fold_weights_kernel(const float* __restrict__ w_m, int64_t ld_m, const float* __
 }
 
 // ---- the GEMM ------------------------------------------------------------------------------
-// Warp roles (416 threads, one CTA per SM, persistent over 128-row tiles):
-//   warps 0-7   producers: cp.async raw K chunks, transform + hi/lo split, write the swizzled A stages
-//   warps 8-11  epilogue:  TMEM -> registers -> global (+ BatchNorm column sums), one TMEM lane quarter each
-//   warp  12    MMA issuer (one lane): tcgen05.mma per 8-float k-step, tcgen05.commit to the barriers
+// Warp roles (800 threads, one CTA per SM, persistent over 128-row tiles):
+//   warps 0-15  producers: cp.async raw K chunks, transform + hi/lo split, write the swizzled A stages
+//   warps 16-23 epilogue:  TMEM -> registers -> global (+ BatchNorm column sums); two warps per TMEM lane
+//               quarter, alternating 16-column blocks
+//   warp  24    MMA issuer (one lane): tcgen05.mma per 8-float k-step, tcgen05.commit to the barriers
+// Every role is latency-bound per warp (short dependent chains between barriers), hence many warps.
 // Hand-offs are mbarriers only: full[s] (producers -> MMA), empty[s] (MMA done -> producers),
 // acc_full[a] (MMA -> epilogue), acc_empty[a] (epilogue -> MMA).  Two A stages and two TMEM
 // accumulators, so loads, conversion, MMAs and the epilogue of consecutive tiles overlap.
 constexpr int kRing = 2;             // raw K-chunk slots (cp.async targets), 16 KB each
-constexpr int kProducerThreads = 256;
-constexpr int kEpilogueThreads = 128;
+constexpr int kProducerWarps = 16;
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kEpilogueThreads = 256;
+constexpr int kItems = 1024 / kProducerThreads;   // float4 items of a chunk per producer thread
 constexpr int kGemmThreads = kProducerThreads + kEpilogueThreads + 32;
+constexpr int kMmaWarp = (kProducerThreads + kEpilogueThreads) / 32;
 
 struct SmemLayout {
   float* w_hi; float* w_lo;
@@ -188,11 +195,14 @@ struct SmemLayout {
   float* col_sq;
   float* bias;                     // [np]
   float* bn;                       // [3][k1] mean | scale | beta of the a1 transform
+  float* stage;                    // optional: 8 epilogue warps x [32][36] transpose buffers (coalesced stores)
   uint64_t* bar;                   // full[2], empty[2], acc_full[2], acc_empty[2]
   uint32_t* tmem_base;
 };
 
-__device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int np, int kp32, int a_stages, int k1) {
+constexpr int kStageFloats = 8 * 32 * 36;
+
+__device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int np, int kp32, int a_stages, int k1, int staged) {
   SmemLayout s;
   float* f = reinterpret_cast<float*>(base);
   s.w_hi = f; f += static_cast<size_t>(np) * kp32;
@@ -209,6 +219,8 @@ __device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int np, in
   s.col_sq = f; f += 8 * np;
   s.bias = f; f += np;
   s.bn = f; f += 3 * k1;
+  s.stage = nullptr;
+  if (staged) { s.stage = f; f += kStageFloats; }
   s.bar = reinterpret_cast<uint64_t*>(f); f += 16;
   s.tmem_base = reinterpret_cast<uint32_t*>(f);
   return s;
@@ -227,7 +239,7 @@ node_gemm_kernel(TcGemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int np = p.np, kp = p.kp, kp32 = (p.kp + 31) & ~31;
   const int a_stages = p.a_stages;
-  const SmemLayout s = carve_smem(smem_raw, np, kp32, a_stages, p.k1);
+  const SmemLayout s = carve_smem(smem_raw, np, kp32, a_stages, p.k1, p.staged_epilogue);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int acc_cols = 2 * np;
   const int tmem_cols = acc_cols <= 32 ? 32 : (acc_cols <= 64 ? 64 : (acc_cols <= 128 ? 128 : (acc_cols <= 256 ? 256 : 512)));
@@ -244,7 +256,7 @@ node_gemm_kernel(TcGemmParams p) {
     mbar_init(&acc_empty[0], kEpilogueThreads); mbar_init(&acc_empty[1], kEpilogueThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s.tmem_base)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -272,8 +284,11 @@ node_gemm_kernel(TcGemmParams p) {
   const int64_t n_tiles = (p.m + kRows - 1) / kRows;
   const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   bool timed_out = false;
+  // optional timeline of CTA 0 (debug): trace[role * 64 + tile * 2 + {0, 1}] = clock64
+  long long* trace = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
+  if (trace != nullptr && tid == 0) trace[3 * 64] = clock64();
 
-  if (warp < 8) {
+  if (warp < kProducerWarps) {
     // =========================== producers ===========================
     // K is laid out segment by segment, each padded to whole 32-float chunks, so a chunk lies in
     // exactly one segment: the segment logic is decided once per chunk, not per element.
@@ -282,11 +297,11 @@ node_gemm_kernel(TcGemmParams p) {
     const uint32_t raw_addr = smem_u32(s.raw);
     const bool has_bn = p.a1_mean != nullptr;
     const int m32 = static_cast<int>(p.m);
-    // chunk-invariant coordinates of this thread's 4 items
-    int rloc[4], kcol[4], off[4];
+    // chunk-invariant coordinates of this thread's items
+    int rloc[kItems], kcol[kItems], off[kItems];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int u = it * 8 + warp;
+    for (int it = 0; it < kItems; ++it) {
+      const int u = it * kProducerWarps + warp;
       const int k4 = ((u & 1) << 2) + kq;
       rloc[it] = (u >> 1) * 8 + r8;
       kcol[it] = k4 * 4;
@@ -295,15 +310,15 @@ node_gemm_kernel(TcGemmParams p) {
     // ---- prefetch stream (runs up to two chunks ahead, possibly already in the next tile) --------
     int64_t pf_tl = 0;
     int pf_kc = 0, pf_slot = 0;
-    const float* pf_a1[4];
-    const float* pf_a2[4];
-    bool pf_ok[4];
+    const float* pf_a1[kItems];
+    const float* pf_a2[kItems];
+    bool pf_ok[kItems];
     auto prefetch = [&]() {
       if (pf_tl < my_tiles) {
         if (pf_kc == 0) {
           const int row0 = static_cast<int>(blockIdx.x + pf_tl * gridDim.x) * kRows;
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
+          for (int it = 0; it < kItems; ++it) {
             const int row = row0 + rloc[it];
             pf_ok[it] = row < m32;
             const int rr = pf_ok[it] ? row : 0;
@@ -318,7 +333,7 @@ node_gemm_kernel(TcGemmParams p) {
         const int col0 = k0 < k1p ? k0 : (seg1 ? k0 - k1p : k0 - k1p - k2p);
         const int seg_len = seg1 ? p.k2 : p.k1;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
+        for (int it = 0; it < kItems; ++it) {
           const bool valid = pf_ok[it] && (col0 + kcol[it] < seg_len);
           const float* src = (seg1 ? pf_a2[it] : pf_a1[it]) + col0;
           cp_async16(slot_addr + off[it] * 4u, valid ? src : p.a1, valid ? 16u : 0u);
@@ -328,15 +343,35 @@ node_gemm_kernel(TcGemmParams p) {
       }
       asm volatile("cp.async.commit_group;" ::: "memory");  // always commit: uniform group accounting
     };
+    // L2 prefetch of a whole tile's A rows, one tile ahead of the cp.async stream: the ring only holds
+    // 32 KB per SM, too little to cover DRAM latency at full bandwidth, but enough for L2 latency.
+    const int lines1 = (p.k1 * 4 + 127) >> 7, lines2 = (p.k2 * 4 + 127) >> 7;
+    auto l2_prefetch_tile = [&](int64_t tl) {
+      if (tl >= my_tiles) return;
+      if (tid >= 256) return;
+      const int row = static_cast<int>(blockIdx.x + tl * gridDim.x) * kRows + (tid & 127);
+      if (row >= m32) return;
+      const int64_t arow = p.a1_rows != nullptr ? p.a1_rows[row] : row;
+      const float* r1 = p.a1 + arow * p.lda1;
+      const float* r2 = p.a2 != nullptr ? p.a2 + static_cast<int64_t>(row) * p.lda2 : nullptr;
+      for (int l = tid >> 7; l < lines1 + lines2; l += 2) {
+        const float* addr = l < lines1 ? r1 + l * 32 : r2 + (l - lines1) * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
+      }
+    };
+    l2_prefetch_tile(0);
+    l2_prefetch_tile(1);
     prefetch();
     prefetch();
     uint32_t g = 0;  // chunk counter of the convert stream
     for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      if (trace != nullptr && tid == 0 && tl < 32) trace[0 * 64 + tl * 2] = clock64();
+      l2_prefetch_tile(tl + 2);
       const int row0 = static_cast<int>(blockIdx.x + tl * gridDim.x) * kRows;
-      bool ok[4];
-      float rs[4];
+      bool ok[kItems];
+      float rs[kItems];
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
+      for (int it = 0; it < kItems; ++it) {
         const int row = row0 + rloc[it];
         ok[it] = row < m32;
         rs[it] = 1.f;
@@ -353,9 +388,9 @@ node_gemm_kernel(TcGemmParams p) {
         const int seg_len = seg1 ? p.k2 : p.k1;
         asm volatile("cp.async.wait_group 1;" ::: "memory");  // this thread's items of chunk g have landed
         const float* raw = s.raw + (g & 1u) * kABufFloats;
-        float4 hi[4], lo[4];
+        float4 hi[kItems], lo[kItems];
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
+        for (int it = 0; it < kItems; ++it) {
           float4 v = *reinterpret_cast<const float4*>(raw + off[it]);
           const int c = col0 + kcol[it];
           const bool valid = ok[it] && c < seg_len;
@@ -384,16 +419,17 @@ node_gemm_kernel(TcGemmParams p) {
         float* dst_hi = s.a_hi[b];
         float* dst_lo = s.a_lo[b];
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
+        for (int it = 0; it < kItems; ++it) {
           *reinterpret_cast<float4*>(dst_hi + off[it]) = hi[it];
           *reinterpret_cast<float4*>(dst_lo + off[it]) = lo[it];
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (MMA)
         mbar_arrive(&full[b]);
       }
+      if (trace != nullptr && tid == 0 && tl < 32) trace[0 * 64 + tl * 2 + 1] = clock64();
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-  } else if (warp == 12) {
+  } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
     // The whole warp runs this loop with uniform control flow and uniform operands (descriptors stay
     // in uniform registers, advancing one is a 32-bit add on its low word); only the tcgen05
@@ -410,6 +446,7 @@ node_gemm_kernel(TcGemmParams p) {
       if (tl >= 2 && !mbar_wait(&acc_empty[ab], static_cast<uint32_t>(((tl >> 1) - 1) & 1))) timed_out = true;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_addr = tmem_d + static_cast<uint32_t>(ab * np);
+      if (trace != nullptr && lane == 0 && tl < 32) trace[1 * 64 + tl * 2] = clock64();
       for (int kc = 0; kc < chunks_per_tile; ++kc, ++g) {
         const uint32_t b = a_stages == 2 ? (g & 1u) : 0u;
         const uint32_t use = a_stages == 2 ? (g >> 1) : g;
@@ -428,15 +465,17 @@ node_gemm_kernel(TcGemmParams p) {
         umma_commit_pred(&empty[b], leader);   // arrives when the MMAs above have finished reading the stage
       }
       umma_commit_pred(&acc_full[ab], leader);  // ... and when the whole tile's accumulator is complete
+      if (trace != nullptr && lane == 0 && tl < 32) trace[1 * 64 + tl * 2 + 1] = clock64();
     }
   } else {
     // =========================== epilogue ===========================
     // thread = row (TMEM lane), 16 columns per tcgen05.ld; each lane stores 4 x 16 bytes of its own
     // row; BatchNorm column sums via a fixed-order butterfly over the warp's 32 rows.
-    const int q = warp - 8;
+    const int ew = warp - kProducerWarps;      // 0..7
+    const int q = ew & 3, half = ew >> 2;      // TMEM lane quarter, parity of the column blocks
     const int n_blocks = np >> 4;
     const bool vec = ((p.ldy & 3) == 0) && ((p.n_store & 3) == 0);
-    const int et = tid - kProducerThreads;  // 0..127
+    const int et = tid - kProducerThreads;     // 0..255
     for (int64_t tl = 0; tl < my_tiles; ++tl) {
       const int ab = static_cast<int>(tl & 1);
       const int64_t tile = blockIdx.x + tl * gridDim.x;
@@ -447,16 +486,76 @@ node_gemm_kernel(TcGemmParams p) {
           ? p.residual + (row_ok ? (p.a1_rows != nullptr ? static_cast<int64_t>(p.a1_rows[row]) : row) : 0) * p.ldr : nullptr;
       if (!mbar_wait(&acc_full[ab], static_cast<uint32_t>((tl >> 1) & 1))) timed_out = true;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (trace != nullptr && et == 0 && tl < 32) trace[2 * 64 + tl * 2] = clock64();
       float* csum = s.col_sum + (ab * 4 + q) * np;
       float* csq = s.col_sq + (ab * 4 + q) * np;
-      for (int cb = 0; cb < n_blocks; ++cb) {
+      if (s.stage != nullptr) {
+        // Coalesced path (no residual / BatchNorm sums): 32 columns at a time through a per-warp
+        // transpose buffer, so that a store instruction writes 4 rows x 128 contiguous bytes instead
+        // of 32 rows x 16 bytes (8x fewer LSU wavefronts; the strided form bounded the kernel).
+        float* st = s.stage + ew * (32 * 36);
+        const int n_dbl = (n_blocks + 1) >> 1;
+        const int64_t tile_row0 = tile * kRows + q * 32;
+        for (int cd = half; cd < n_dbl; cd += 2) {
+          uint32_t r0[16], r1[16];
+          const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ab * np + cd * 32);
+          const bool second = cd * 2 + 1 < n_blocks;
+          tmem_ld16(taddr, r0);
+          if (second) tmem_ld16(taddr + 16, r1);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bv = *reinterpret_cast<const float4*>(s.bias + cd * 32 + j4 * 4);
+            *reinterpret_cast<float4*>(st + lane * 36 + j4 * 4) =
+                make_float4(__uint_as_float(r0[j4 * 4]) + bv.x, __uint_as_float(r0[j4 * 4 + 1]) + bv.y,
+                            __uint_as_float(r0[j4 * 4 + 2]) + bv.z, __uint_as_float(r0[j4 * 4 + 3]) + bv.w);
+          }
+          if (second) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bv = *reinterpret_cast<const float4*>(s.bias + cd * 32 + 16 + j4 * 4);
+              *reinterpret_cast<float4*>(st + lane * 36 + 16 + j4 * 4) =
+                  make_float4(__uint_as_float(r1[j4 * 4]) + bv.x, __uint_as_float(r1[j4 * 4 + 1]) + bv.y,
+                              __uint_as_float(r1[j4 * 4 + 2]) + bv.z, __uint_as_float(r1[j4 * 4 + 3]) + bv.w);
+            }
+          }
+          __syncwarp();
+          const int c4 = lane & 7, rsub = lane >> 3;
+          const int col = cd * 32 + c4 * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rl = it * 4 + rsub;
+            const int64_t grow = tile_row0 + rl;
+            if (grow < p.m && col < p.n_store) {
+              float4 v4 = *reinterpret_cast<const float4*>(st + rl * 36 + c4 * 4);
+              if (col + 3 >= p.n) {  // padding columns are written as exact zeros
+                if (col + 0 >= p.n) v4.x = 0.f;
+                if (col + 1 >= p.n) v4.y = 0.f;
+                if (col + 2 >= p.n) v4.z = 0.f;
+                if (col + 3 >= p.n) v4.w = 0.f;
+              }
+              *reinterpret_cast<float4*>(p.y + grow * p.ldy + col) = v4;
+            }
+          }
+          __syncwarp();
+        }
+      } else
+      for (int cb = half; cb < n_blocks; cb += 2) {
         uint32_t r[16];
         tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ab * np + cb * 16), r);
         float v[16];
+        const bool full_block = cb * 16 + 16 <= p.n;   // no padding columns inside this block
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = cb * 16 + j;
-          v[j] = col < p.n ? __uint_as_float(r[j]) + s.bias[col] : 0.f;
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 bv = *reinterpret_cast<const float4*>(s.bias + cb * 16 + j4 * 4);  // zero beyond n
+          v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) + bv.x;
+          v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) + bv.y;
+          v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) + bv.z;
+          v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) + bv.w;
+        }
+        if (!full_block) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (cb * 16 + j >= p.n) v[j] = 0.f;
         }
         if (rrow != nullptr && row_ok) {
 #pragma unroll
@@ -475,7 +574,8 @@ node_gemm_kernel(TcGemmParams p) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const int col = cb * 16 + j4 * 4;
-              if (col < p.n_store) *reinterpret_cast<float4*>(yrow + col) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+              if (full_block || col < p.n_store)
+                *reinterpret_cast<float4*>(yrow + col) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
             }
           } else {
 #pragma unroll
@@ -513,8 +613,9 @@ node_gemm_kernel(TcGemmParams p) {
       // accumulator drained: hand it back to the MMA issuer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&acc_empty[ab]);
+      if (trace != nullptr && et == 0 && tl < 32) trace[2 * 64 + tl * 2 + 1] = clock64();
       if (p.bn_partial != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four quarters' column sums are in shared memory
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the four quarters' column sums are in shared memory
         const float* cs = s.col_sum + ab * 4 * np;
         const float* cq = s.col_sq + ab * 4 * np;
         for (int c = et; c < p.n; c += kEpilogueThreads) {
@@ -529,17 +630,19 @@ node_gemm_kernel(TcGemmParams p) {
     }
   }
 
+  if (trace != nullptr && tid == 0) trace[3 * 64 + 1] = clock64();
   if (timed_out && p.status != nullptr) atomicExch(p.status, RGNN_ERR_CUDA);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 12) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
   }
 }
 
-size_t smem_bytes_for(int np, int kp, int a_stages) {
+size_t smem_bytes_for(int np, int kp, int a_stages, int staged = 0) {
   const size_t kp32 = (static_cast<size_t>(kp) + 31) & ~static_cast<size_t>(31);
-  return sizeof(float) * (2 * np * kp32 + (2 * a_stages + kRing) * kABufFloats + 16 * np + np + 3 * kp32 + 32 + 4) + 64;
+  return sizeof(float) * (2 * np * kp32 + (2 * a_stages + kRing) * kABufFloats + 16 * np + np + 3 * kp32 + 32 + 4 +
+                          (staged ? kStageFloats : 0)) + 64;
 }
 
 int pick_a_stages(int np, int kp) {
@@ -584,14 +687,27 @@ int tc_pack_weights(const TcWeightBlocks& blocks, const TcGemmShape& sh, float* 
   return RGNN_OK;
 }
 
+// debug: device buffer of 4 * 64 int64 receiving CTA 0's timeline of the NEXT launch whose tag matches
+static long long* g_trace_buffer = nullptr;
+static char g_trace_tag[64] = "";
+extern "C" void rgnn_debug_trace_node_gemm(void* device_buffer, const char* tag) {
+  g_trace_buffer = static_cast<long long*>(device_buffer);
+  snprintf(g_trace_tag, sizeof(g_trace_tag), "%s", tag != nullptr ? tag : "");
+}
+
 int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
   if (p.m <= 0) return RGNN_OK;
+  if (g_trace_buffer != nullptr && strcmp(tag, g_trace_tag) == 0) { p.trace = g_trace_buffer; g_trace_buffer = nullptr; }
   p.np = tc_padded_n(p.n);
   p.kp = tc_padded_k(p.k1, p.k2, p.k3);
   if (p.n_store < p.n) p.n_store = p.n;
   p.a_stages = pick_a_stages(p.np, p.kp);
   if (p.a_stages == 0) return RGNN_ERR_UNSUPPORTED;
-  const size_t smem = smem_bytes_for(p.np, p.kp, p.a_stages);
+  // coalesced (staged) epilogue when there is neither residual nor BatchNorm sums, the rows allow
+  // 16-byte stores and the transpose buffers still fit
+  p.staged_epilogue = (p.residual == nullptr && p.bn_partial == nullptr && (p.ldy & 3) == 0 && (p.n_store & 3) == 0 &&
+                       smem_bytes_for(p.np, p.kp, p.a_stages, 1) <= 227 * 1024) ? 1 : 0;
+  const size_t smem = smem_bytes_for(p.np, p.kp, p.a_stages, p.staged_epilogue);
   static size_t configured = 0;
   if (smem > configured) {
     RGNN_CUDA_CHECK(cudaFuncSetAttribute(node_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -39,7 +39,7 @@ struct TcGemmParams {
   const float* a1_mean = nullptr; const float* a1_scale = nullptr; const float* a1_beta = nullptr;
   int32_t relu_a1 = 0, relu_a2 = 0;
   const float* wpack = nullptr;                                  // tc_pack_weights image
-  int32_t n = 0, np = 0, kp = 0, a_stages = 0;
+  int32_t n = 0, np = 0, kp = 0, a_stages = 0, staged_epilogue = 0;
   const float* bias = nullptr;
   const float* residual = nullptr; int64_t ldr = 0;
   const float* res_mean = nullptr; const float* res_scale = nullptr; const float* res_beta = nullptr;
@@ -48,6 +48,7 @@ struct TcGemmParams {
   double* bn_partial = nullptr;                                  // [tc_tiles(m)][2][n] column sums / squares
   int64_t m = 0;
   int32_t* status = nullptr;                                     // device flag set if a barrier wait timed out
+  long long* trace = nullptr;                                    // debug timeline of CTA 0 (node_gemm.cu)
 };
 
 bool tc_gemm_supported(const TcGemmShape& sh);

@@ -39,24 +39,28 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int dist
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base;
-  if (tid == 0) {
-    const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 64 * 1024);
+  if (warp == 0) {
+    // warp-uniform issue loop (descriptors in uniform registers), lane 0 issues; 16 MMAs per iteration
+    const uint32_t leader = (tid == 0) ? 1u : 0u;
+    const uint64_t da0 = umma_desc(smem_u32(smem)), db0 = umma_desc(smem_u32(smem + 64 * 1024));
     const uint32_t id = idesc(KIND == 0 ? 2 : 1, 128, n);
     const long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) {
-      // `distinct` different 32-byte k-steps inside the 128-byte swizzle atom / further panels
-      const int j = i % distinct;
-      const uint64_t da = umma_desc(a_addr + (j & 3) * 32 + (j >> 2) * 16384);
-      const uint64_t db = umma_desc(b_addr + (j & 3) * 32 + (j >> 2) * 32768);
-      if (KIND == 0) {
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-                     ::"r"(tmem_d), "l"(da), "l"(db), "r"(id), "r"(i > 0 ? 1u : 0u) : "memory");
-      } else {
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-                     ::"r"(tmem_d), "l"(da), "l"(db), "r"(id), "r"(i > 0 ? 1u : 0u) : "memory");
+    for (int i = 0; i < iters; i += 16) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const uint64_t da = da0 + 2 * (u & 3) * (distinct > 1 ? 1 : 0);
+        const uint64_t db = db0 + 2 * (u & 3) * (distinct > 1 ? 1 : 0);
+        if (KIND == 0) {
+          asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                       ::"r"(tmem_d), "l"(da), "l"(db), "r"(id), "r"(1u), "r"(leader) : "memory");
+        } else {
+          asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                       ::"r"(tmem_d), "l"(da), "l"(db), "r"(id), "r"(1u), "r"(leader) : "memory");
+        }
       }
     }
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    if (tid == 0)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     const long long t1 = clock64();
     uint32_t done = 0;
     while (!done) {
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int dist
                    : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
     }
     const long long t2 = clock64();
-    if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    if (blockIdx.x == 0 && tid == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -81,7 +85,7 @@ int main() {
   for (int kind = 0; kind < 2; ++kind)
     for (int grid : {1, 148})
       for (int n : {16, 64, 128, 144, 256})
-        for (int distinct : {1, 4, 8}) {
+        for (int distinct : {1, 4}) {
           for (int rep = 0; rep < 2; ++rep) {
             if (kind == 0) rate_kernel<0><<<grid, 128, smem>>>(n, iters, distinct, out);
             else rate_kernel<1><<<grid, 128, smem>>>(n, iters, distinct, out);

@@ -1,0 +1,28 @@
+"""Debug: timeline (clock64 cycles) of CTA 0 of the tcgen05 node GEMM inside the fused path."""
+import ctypes as C, sys
+import numpy as np, torch
+sys.path.insert(0, ".")
+from radargnn_b200 import ops, synthetic, _lib
+from scripts.time_pipeline import make_cfg
+lib = _lib.load()
+fn = lib.rgnn_debug_trace_node_gemm
+fn.argtypes = [C.c_void_p, C.c_char_p]; fn.restype = None
+n = 100_000
+fr = synthetic.uniform_square(n, seed=0)
+pos = torch.from_numpy(fr.X_cc).float().cuda(); vel = torch.from_numpy(fr.V_cc_compensated).float().cuda()
+x0 = torch.from_numpy(synthetic.node_embeddings(n, 64)).cuda()
+cfg = make_cfg()
+for _ in range(3):
+    ops.pipeline_forward(cfg, pos, vel, x0)
+for tag in (b"node_gemm_pre", b"node_gemm_post"):
+    buf = torch.zeros(4 * 64, dtype=torch.int64, device="cuda")
+    fn(buf.data_ptr(), tag)
+    ops.pipeline_forward(cfg, pos, vel, x0)
+    torch.cuda.synchronize()
+    t = buf.cpu().numpy().reshape(4, 32, 2)
+    t0 = t[3, 0, 0]
+    print(tag.decode(), "kernel cycles (CTA 0):", t[3, 0, 1] - t0)
+    for tl in range(8):
+        if t[0, tl, 0] == 0: break
+        row = [int(v - t0) for v in (t[0, tl, 0], t[0, tl, 1], t[1, tl, 0], t[1, tl, 1], t[2, tl, 0], t[2, tl, 1])]
+        print(f"  tile {tl}: producer {row[0]:7d}..{row[1]:7d}  mma {row[2]:7d}..{row[3]:7d}  epilogue {row[4]:7d}..{row[5]:7d}")
