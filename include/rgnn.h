@@ -202,7 +202,17 @@ typedef struct rgnn_conv_desc {
   const float* pre_bias[RGNN_MAX_MLP_LAYERS];
   const float* post_weight[RGNN_MAX_MLP_LAYERS];
   const float* post_bias[RGNN_MAX_MLP_LAYERS];
+  /* Optional (may be NULL): tensor-core weight images made by rgnn_conv_pack_weights for exactly these
+   * weights.  NULL = the images are rebuilt inside every forward call (weights are then read at call
+   * time, as the reference's tests require); callers whose weights are unchanged between calls pack once. */
+  const void* packed_weights;
 } rgnn_conv_desc;
+
+/* Bytes of the packed images of a layer (0 when the layer does not use the tensor-core path), and the
+ * packing itself: hi/lo TF32 split of W_s and of the update weights with W_m W_t folded in, laid out
+ * as 128-byte-swizzled K-major panels (radargnn_b200/csrc/node_gemm.cu). */
+size_t rgnn_conv_packed_bytes(const rgnn_conv_desc* desc);
+int rgnn_conv_pack_weights(const rgnn_conv_desc* desc, void* packed, size_t packed_bytes, rgnn_stream_t stream);
 
 size_t rgnn_conv_workspace_bytes(const rgnn_conv_desc* desc, int64_t n_nodes, int64_t n_edges);
 int rgnn_conv_forward(const rgnn_conv_desc* desc, const float* x, int64_t n_nodes,

@@ -45,6 +45,7 @@ class ConvDesc(C.Structure):
         ("edge_encoder_weight", C.c_void_p), ("edge_encoder_bias", C.c_void_p),
         ("pre_weight", C.c_void_p * MAX_MLP_LAYERS), ("pre_bias", C.c_void_p * MAX_MLP_LAYERS),
         ("post_weight", C.c_void_p * MAX_MLP_LAYERS), ("post_bias", C.c_void_p * MAX_MLP_LAYERS),
+        ("packed_weights", C.c_void_p),
     ]
 
 
@@ -97,6 +98,8 @@ _PROTOTYPES = {
     "rgnn_csc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "rgnn_csc_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rgnn_conv_packed_bytes": (C.c_size_t, [C.POINTER(ConvDesc)]),
+    "rgnn_conv_pack_weights": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     "rgnn_conv_workspace_bytes": (C.c_size_t, [C.POINTER(ConvDesc), C.c_int64, C.c_int64]),
     "rgnn_conv_forward": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t,

@@ -67,12 +67,19 @@ edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, 
                       IsolatedNodeTerm iso) {
   extern __shared__ float w_s[];  // [de][pp] (DE == 0 only)
   if (DE == 0) stage_edge_weights(w_e, ldwe, p, pp, de, w_s);
+  // kSplit = 2 would let two adjacent lanes share a (node, chunk), one on the even slots and one on
+  // the odd ones, combined with a shuffle.  Measured slower (0.66 vs 0.49 ms per step at the headline
+  // size): the kernel is bound by instruction issue / L1 wavefronts, not by gathers in flight.
+  constexpr int kSplit = 1;
   const int chunks = pp >> 2;
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t node = gid / chunks;
-  if (node >= n_nodes) return;
-  const int c0 = static_cast<int>(gid - node * chunks) << 2;
-  const int beg = csc_ptr[node], end = csc_ptr[node + 1];
+  const int64_t node = gid / (chunks * kSplit);
+  const bool live = node < n_nodes;
+  const int rem = static_cast<int>(gid - node * (chunks * kSplit));
+  const int c0 = (kSplit == 2 ? rem >> 1 : rem) << 2;
+  const int part = kSplit == 2 ? (rem & 1) : 0;
+  const int seg_beg = live ? csc_ptr[node] : 0, seg_end = live ? csc_ptr[node + 1] : 0;
+  const int beg = seg_beg + part, end = seg_end;
 
   float4 wreg[DE > 0 ? DE : 1];
   if (DE > 0) {
@@ -86,7 +93,7 @@ edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, 
   }
 
   float4 base = make_float4(0.f, 0.f, 0.f, 0.f);  // A_n + b for this chunk
-  if (a != nullptr) base = ld4(a + node * pp + c0);
+  if (a != nullptr && live) base = ld4(a + node * pp + c0);
   {
     float4 bb;
     bb.x = c0 + 0 < p ? bias[c0 + 0] : 0.f;
@@ -128,14 +135,14 @@ edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, 
   const float* bcol = b + c0;
   int slot = beg;
   // 4 gathers in flight per thread
-  for (; slot + 4 <= end; slot += 4) {
-    const int s0 = csc_src[slot], s1 = csc_src[slot + 1], s2 = csc_src[slot + 2], s3 = csc_src[slot + 3];
+  for (; slot + 3 * kSplit < end; slot += 4 * kSplit) {
+    const int s0 = csc_src[slot], s1 = csc_src[slot + kSplit], s2 = csc_src[slot + 2 * kSplit], s3 = csc_src[slot + 3 * kSplit];
     float4 v0 = ld4(bcol + static_cast<int64_t>(s0) * pp);
     float4 v1 = ld4(bcol + static_cast<int64_t>(s1) * pp);
     float4 v2 = ld4(bcol + static_cast<int64_t>(s2) * pp);
     float4 v3 = ld4(bcol + static_cast<int64_t>(s3) * pp);
-    v0 = edge_term(slot, v0); v1 = edge_term(slot + 1, v1);
-    v2 = edge_term(slot + 2, v2); v3 = edge_term(slot + 3, v3);
+    v0 = edge_term(slot, v0); v1 = edge_term(slot + kSplit, v1);
+    v2 = edge_term(slot + 2 * kSplit, v2); v3 = edge_term(slot + 3 * kSplit, v3);
     if (MODE == RGNN_AGGR_MAX) acc = max4(acc, max4(max4(v0, v1), max4(v2, v3)));
     else if (MODE == RGNN_AGGR_MIN) acc = min4(acc, min4(min4(v0, v1), min4(v2, v3)));
     else if (MODE == -1) {
@@ -147,7 +154,7 @@ edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, 
       acc = add4(acc, v0); acc = add4(acc, v1); acc = add4(acc, v2); acc = add4(acc, v3);
     }
   }
-  for (; slot < end; ++slot) {
+  for (; slot < end; slot += kSplit) {
     float4 v = ld4(bcol + static_cast<int64_t>(csc_src[slot]) * pp);
     v = edge_term(slot, v);
     if (MODE == RGNN_AGGR_MAX) acc = max4(acc, v);
@@ -156,7 +163,16 @@ edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, 
     else acc = add4(acc, v);
   }
   if (MODE == -1) return;
-  const int deg = end - beg;
+  if (kSplit == 2) {  // combine the even-slot and odd-slot halves (fixed order: deterministic)
+    float4 o;
+    o.x = __shfl_xor_sync(0xffffffffu, acc.x, 1); o.y = __shfl_xor_sync(0xffffffffu, acc.y, 1);
+    o.z = __shfl_xor_sync(0xffffffffu, acc.z, 1); o.w = __shfl_xor_sync(0xffffffffu, acc.w, 1);
+    if (MODE == RGNN_AGGR_MAX) acc = max4(acc, o);
+    else if (MODE == RGNN_AGGR_MIN) acc = min4(acc, o);
+    else acc = part == 0 ? add4(acc, o) : add4(o, acc);
+  }
+  if (!live || part != 0) return;
+  const int deg = seg_end - seg_beg;
   float4 r = make_float4(0.f, 0.f, 0.f, 0.f);  // torch_scatter: empty segments aggregate to 0
   if (deg == 0 && iso.w_t != nullptr) {
     // Folded formulation (node_gemm.cu): the update weights carry W_m W_t for every node, so a
@@ -279,6 +295,45 @@ int launch_edge_aggregate(const float* a, const float* b, const ConvShape& s, co
 
 }  // namespace
 
+// ---- tensor-core weight images -----------------------------------------------------------------
+struct PackedLayout { size_t pre_off, post_off, fold_off, total; };
+
+static PackedLayout packed_layout(const rgnn_conv_desc& d, const ConvShape& s) {
+  PackedLayout pl{};
+  size_t off = 0;
+  pl.pre_off = off; off += align_up(sizeof(float) * tc_pack_floats(conv_pre_shape(s)));
+  pl.post_off = off; off += align_up(sizeof(float) * tc_pack_floats(conv_post_shape(d, s)));
+  pl.fold_off = off; off += align_up(sizeof(float) * static_cast<size_t>(s.c_out) * s.c);
+  pl.total = off;
+  return pl;
+}
+
+// W_s image for B = x W_s^T and the update image [W_x (+ W_m W_t) | W_m | (add: W_m W_t)]
+static int pack_conv_weights(const rgnn_conv_desc& d, const ConvShape& s, float* wpack_pre, float* wpack_post,
+                             float* w_fold, cudaStream_t stream) {
+  const bool mpnn = d.conv_type == RGNN_CONV_MPNN;
+  const int x_s_off = mpnn ? s.c : 0;
+  TcWeightBlocks wb{};
+  wb.count = 1;
+  wb.block[0] = {d.pre_weight[0] + x_s_off, s.p, s.p, s.c, 0, 0};
+  RGNN_RETURN_IF_ERROR(tc_pack_weights(wb, conv_pre_shape(s), wpack_pre, stream));
+  const int64_t ldpost = s.c + s.p;
+  wb.count = 2;
+  wb.block[0] = {d.post_weight[0], ldpost, s.c_out, s.c, 0, 0};
+  wb.block[1] = {d.post_weight[0] + s.c, ldpost, s.c_out, s.p, tc_seg_pad(s.c), 0};  // segments start on 32-float chunks
+  if (mpnn) {
+    RGNN_RETURN_IF_ERROR(tc_fold_weights(d.post_weight[0] + s.c, ldpost, d.pre_weight[0], s.p, s.c_out, s.p, s.c,
+                                         w_fold, stream));
+    wb.count = 3;
+    if (d.aggr == RGNN_AGGR_ADD) {
+      wb.block[2] = {w_fold, s.c, s.c_out, s.c, tc_seg_pad(s.c) + tc_seg_pad(s.pp), 0};   // deg * x segment
+    } else {
+      wb.block[2] = {w_fold, s.c, s.c_out, s.c, 0, 1};            // added onto W_x: (W_x + W_m W_t) x
+    }
+  }
+  return tc_pack_weights(wb, conv_post_shape(d, s), wpack_post, stream);
+}
+
 int conv_shape(const rgnn_conv_desc& d, ConvShape* s) {
   if (d.in_channels < 1 || d.out_channels < 1 || d.edge_dim < 0) return RGNN_ERR_INVALID_ARGUMENT;
   if (d.pre_layers < 1 || d.pre_layers > RGNN_MAX_MLP_LAYERS || d.post_layers < 1 || d.post_layers > RGNN_MAX_MLP_LAYERS)
@@ -350,33 +405,25 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
   const bool aligned = (in.ldx % 4 == 0) && (reinterpret_cast<uintptr_t>(in.x) % 16 == 0) &&
                        (in.mean == nullptr || reinterpret_cast<uintptr_t>(in.mean) % 16 == 0);
   if (w.tc_post && aligned) {
-    // weight images (weights may have changed since the last call: repacked every forward)
-    TcWeightBlocks wb{};
-    wb.count = 1;
-    wb.block[0] = {d.pre_weight[0] + x_s_off, s.p, s.p, s.c, 0, 0};
-    RGNN_RETURN_IF_ERROR(tc_pack_weights(wb, conv_pre_shape(s), w.wpack_pre, stream));
-    const int64_t ldpost = s.c + s.p;
-    wb.count = 2;
-    wb.block[0] = {d.post_weight[0], ldpost, s.c_out, s.c, 0, 0};
-    wb.block[1] = {d.post_weight[0] + s.c, ldpost, s.c_out, s.p, tc_seg_pad(s.c), 0};  // segments start on 32-float chunks
+    // weight images: the caller's pre-packed buffer, or (weights may have changed since the last call)
+    // repacked into the workspace on every forward
+    const float* wpack_pre = w.wpack_pre;
+    const float* wpack_post = w.wpack_post;
     const bool third_segment = mpnn && d.aggr == RGNN_AGGR_ADD;
-    if (mpnn) {
-      RGNN_RETURN_IF_ERROR(tc_fold_weights(d.post_weight[0] + s.c, ldpost, d.pre_weight[0], s.p, s.c_out, s.p, s.c,
-                                           w.w_fold, stream));
-      wb.count = 3;
-      if (third_segment) {
-        wb.block[2] = {w.w_fold, s.c, s.c_out, s.c, tc_seg_pad(s.c) + tc_seg_pad(s.pp), 0};   // deg * x segment
-      } else {
-        wb.block[2] = {w.w_fold, s.c, s.c_out, s.c, 0, 1};            // added onto W_x: (W_x + W_m W_t) x
-      }
+    if (d.packed_weights != nullptr) {
+      const PackedLayout pl = packed_layout(d, s);
+      const char* base = static_cast<const char*>(d.packed_weights);
+      wpack_pre = reinterpret_cast<const float*>(base + pl.pre_off);
+      wpack_post = reinterpret_cast<const float*>(base + pl.post_off);
+    } else {
+      RGNN_RETURN_IF_ERROR(pack_conv_weights(d, s, w.wpack_pre, w.wpack_post, w.w_fold, stream));
     }
-    RGNN_RETURN_IF_ERROR(tc_pack_weights(wb, conv_post_shape(d, s), w.wpack_post, stream));
     RGNN_CUDA_CHECK(cudaMemsetAsync(w.tc_status, 0, sizeof(int32_t), stream));
 
     TcGemmParams g1;
     g1.a1 = in.x; g1.lda1 = in.ldx; g1.k1 = s.c; g1.a1_rows = in.rows;
     g1.a1_mean = in.mean; g1.a1_scale = in.scale; g1.a1_beta = in.beta; g1.relu_a1 = in.relu;
-    g1.wpack = w.wpack_pre; g1.n = s.p; g1.n_store = s.pp;
+    g1.wpack = wpack_pre; g1.n = s.p; g1.n_store = s.pp;
     g1.y = w.b; g1.ldy = s.pp; g1.m = n_nodes; g1.status = w.tc_status;
     RGNN_RETURN_IF_ERROR(launch_tc_gemm(g1, "node_gemm_pre", stream));
 
@@ -401,7 +448,7 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
     g2.a1_mean = in.mean; g2.a1_scale = in.scale; g2.a1_beta = in.beta; g2.relu_a1 = in.relu;
     g2.a2 = w.m; g2.lda2 = s.pp; g2.k2 = s.pp;
     if (third_segment) { g2.k3 = s.c; g2.csc_ptr = csc_ptr; g2.rowscale_mode = 2; }
-    g2.wpack = w.wpack_post; g2.n = s.c_out; g2.n_store = s.c_out; g2.bias = d.post_bias[0];
+    g2.wpack = wpack_post; g2.n = s.c_out; g2.n_store = s.c_out; g2.bias = d.post_bias[0];
     g2.y = first_out; g2.ldy = s.c_out; g2.m = n_nodes; g2.status = w.tc_status;
     if (!mpnn && d.post_layers == 1) {
       g2.residual = in.x; g2.ldr = in.ldx;
@@ -513,6 +560,31 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
 using namespace rgnn;
 
 extern "C" {
+
+size_t rgnn_conv_packed_bytes(const rgnn_conv_desc* desc) {
+  if (desc == nullptr) return 0;
+  rgnn_conv_desc d = *desc;
+  static const float dummy = 0.f;
+  for (int l = 0; l < RGNN_MAX_MLP_LAYERS; ++l) d.pre_weight[l] = d.pre_bias[l] = d.post_weight[l] = d.post_bias[l] = &dummy;
+  d.edge_encoder_weight = d.edge_encoder_bias = &dummy;
+  ConvShape s;
+  if (conv_shape(d, &s) != RGNN_OK || s.general) return 0;
+  if (!tc_gemm_supported(conv_pre_shape(s)) || !tc_gemm_supported(conv_post_shape(d, s))) return 0;
+  return packed_layout(d, s).total;
+}
+
+int rgnn_conv_pack_weights(const rgnn_conv_desc* desc, void* packed, size_t packed_bytes, rgnn_stream_t stream) {
+  if (desc == nullptr || packed == nullptr) return RGNN_ERR_INVALID_ARGUMENT;
+  ConvShape s;
+  RGNN_RETURN_IF_ERROR(conv_shape(*desc, &s));
+  const size_t need = rgnn_conv_packed_bytes(desc);
+  if (need == 0) return RGNN_ERR_UNSUPPORTED;
+  if (packed_bytes < need || reinterpret_cast<uintptr_t>(packed) % 16 != 0) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  const PackedLayout pl = packed_layout(*desc, s);
+  char* base = static_cast<char*>(packed);
+  return pack_conv_weights(*desc, s, reinterpret_cast<float*>(base + pl.pre_off), reinterpret_cast<float*>(base + pl.post_off),
+                           reinterpret_cast<float*>(base + pl.fold_off), static_cast<cudaStream_t>(stream));
+}
 
 size_t rgnn_conv_workspace_bytes(const rgnn_conv_desc* desc, int64_t n_nodes, int64_t n_edges) {
   ConvShape s;

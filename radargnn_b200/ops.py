@@ -205,8 +205,18 @@ class ConvParams:
     pre: List[Tuple[torch.Tensor, torch.Tensor]]    # (weight, bias) of every Linear in pre_mlp
     post: List[Tuple[torch.Tensor, torch.Tensor]]
     edge_encoder: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+    # tensor-core weight images, rebuilt only when a weight tensor was replaced or modified in place
+    # (the key holds every tensor's address and torch version counter)
+    _packed: Optional[torch.Tensor] = None
+    _packed_key: Optional[tuple] = None
 
-    def desc(self, keep: list) -> _lib.ConvDesc:
+    def _tensors(self):
+        out = [t for pair in self.pre + self.post for t in pair]
+        if self.edge_encoder is not None:
+            out += list(self.edge_encoder)
+        return out
+
+    def desc(self, keep: list, pack: bool = True) -> _lib.ConvDesc:
         if self.aggr not in _lib.AGGR:
             raise ValueError(f"unsupported aggregation {self.aggr!r}")
         if len(self.pre) > _lib.MAX_MLP_LAYERS or len(self.post) > _lib.MAX_MLP_LAYERS:
@@ -233,6 +243,19 @@ class ConvParams:
             d.post_weight[i], d.post_bias[i] = dev(w), dev(b)
         if self.edge_encoder is not None:
             d.edge_encoder_weight, d.edge_encoder_bias = dev(self.edge_encoder[0]), dev(self.edge_encoder[1])
+        if pack:
+            lib = _lib.load()
+            nbytes = lib.rgnn_conv_packed_bytes(C.byref(d))
+            if nbytes > 0:
+                key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in self._tensors()) + (self.aggr,)
+                if self._packed is None or self._packed_key != key or self._packed.numel() < nbytes:
+                    device = self.pre[0][0].device
+                    buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+                    with torch.cuda.device(device):
+                        _lib.check(lib.rgnn_conv_pack_weights(C.byref(d), buf.data_ptr(), nbytes, _lib.stream_ptr()))
+                    self._packed, self._packed_key = buf, key
+                keep.append(self._packed)
+                d.packed_weights = self._packed.data_ptr()
         return d
 
 

@@ -80,8 +80,11 @@ def test_workspace_sizes_are_monotone_and_aligned(lib):
     w1 = lib.rgnn_conv_workspace_bytes(C.byref(d), 100_000, 1_600_000)
     # A, B, M [N, 132] fp32 + edge attributes in slot order
     assert w1 >= 3 * 100_000 * 132 * 4 + 1_600_000 * 2 * 4
-    d.pre_layers = 2
-    assert lib.rgnn_conv_workspace_bytes(C.byref(d), 100_000, 1_600_000) > w1 + 2 * 1_600_000 * 132 * 4 - 1
+    # tensor-core weight images of the factored path: W_s [144 x 64] and update [64 x 224], hi + lo
+    assert lib.rgnn_conv_packed_bytes(C.byref(d)) >= 2 * 4 * (144 * 64 + 64 * 224)
+    d.pre_layers = 2   # general path: two [E, 132] per-edge activation buffers, no tensor-core images
+    assert lib.rgnn_conv_packed_bytes(C.byref(d)) == 0
+    assert lib.rgnn_conv_workspace_bytes(C.byref(d), 100_000, 1_600_000) > w1 + 2 * 1_600_000 * 132 * 4 - (4 << 20)
     d.aggr = 17
     assert lib.rgnn_conv_workspace_bytes(C.byref(d), 10, 10) == 0
     assert lib.rgnn_batchnorm_workspace_bytes(100_000, 64) > 0
