@@ -5,6 +5,7 @@
 // csc_src [E] (source node of every slot) and csc_eid [E] (edge id, ascending inside a
 // segment, so that sum / mean aggregate in a fixed order and are run-to-run deterministic).
 #include "csc.cuh"
+#include "edge_feature_math.cuh"
 
 namespace rgnn {
 namespace {
@@ -27,6 +28,27 @@ fill_slots_kernel(const int64_t* __restrict__ edge_index, int64_t n_edges, const
   const int pos = csc_ptr[t] + atomicAdd(&cursor[t], 1);
   csc_eid[pos] = static_cast<int32_t>(e);
   csc_src[pos] = static_cast<int32_t>(s);
+}
+
+__global__ void __launch_bounds__(256)
+fill_slots_features_kernel(const int64_t* __restrict__ edge_index, int64_t n_edges, const int32_t* __restrict__ csc_ptr,
+                           int32_t* __restrict__ cursor, int32_t* __restrict__ csc_src, int32_t* __restrict__ csc_eid,
+                           const int32_t* __restrict__ node_map, FusedEdgeAttr f) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int64_t i = edge_index[e], j = edge_index[n_edges + e];
+  int64_t t = j, s = i;
+  if (node_map != nullptr) { t = node_map[t]; s = node_map[s]; }
+  const int slot = csc_ptr[t] + atomicAdd(&cursor[t], 1);
+  csc_eid[slot] = static_cast<int32_t>(e);
+  csc_src[slot] = static_cast<int32_t>(s);
+  double xi[4], xj[4], vi[4], vj[4];
+  efm::load_vec(f.pos, i, 2, xi);
+  efm::load_vec(f.pos, j, 2, xj);
+  efm::load_vec(f.vel, i, 2, vi);
+  efm::load_vec(f.vel, j, 2, vj);
+  efm::write_edge_row<float>(xi, xj, vi, vj, 2, 2, f.spec, f.error_flag, f.edge_attr + e * f.spec.width,
+                             f.ea_csc + static_cast<int64_t>(slot) * f.spec.width);
 }
 
 // one thread per target: order the segment by edge id (segments are short: in-degree)
@@ -86,6 +108,26 @@ int csc_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, bool 
     sort_segments_kernel<<<div_up(n_nodes, 128), 128, 0, stream>>>(csc_ptr, n_nodes, csc_src, csc_eid);
     RGNN_LAUNCH_CHECK();
   }
+  return RGNN_OK;
+}
+
+int csc_build_fused(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, bool counts_ready,
+                    const CscWorkspace& w, int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid, cudaStream_t stream,
+                    const int32_t* node_map, const FusedEdgeAttr& fea) {
+  RGNN_PROFILE("csc_build_edge_attr", stream);
+  if (!counts_ready) {
+    RGNN_CUDA_CHECK(cudaMemsetAsync(w.count, 0, sizeof(int32_t) * (n_nodes + 1), stream));
+    if (n_edges > 0) {
+      count_targets_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index + n_edges, n_edges, w.count, node_map);
+      RGNN_LAUNCH_CHECK();
+    }
+  }
+  RGNN_RETURN_IF_ERROR(exclusive_scan_i32(w.count, csc_ptr, n_nodes, w.scan_scratch, stream));
+  if (n_edges == 0) return RGNN_OK;
+  RGNN_CUDA_CHECK(cudaMemsetAsync(w.cursor, 0, sizeof(int32_t) * (n_nodes + 1), stream));
+  fill_slots_features_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index, n_edges, csc_ptr, w.cursor, csc_src,
+                                                                      csc_eid, node_map, fea);
+  RGNN_LAUNCH_CHECK();
   return RGNN_OK;
 }
 

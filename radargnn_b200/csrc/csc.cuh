@@ -2,6 +2,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "features.cuh"
 
 namespace rgnn {
 
@@ -27,5 +28,20 @@ inline CscWorkspace carve_csc_workspace(ArenaT& a, int64_t n_nodes) {
 int csc_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, bool counts_ready, bool ordered,
               const CscWorkspace& w, int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid, cudaStream_t stream,
               const int32_t* node_map = nullptr);
+
+// Fused variant for the pipeline (unordered segments only): the slot-fill pass also computes the edge
+// attributes (fp64 arithmetic, f32 output) and writes them twice -- edge_attr [E, De] in the caller's
+// edge order and ea_csc [E, De] in slot order -- saving the separate feature and gather passes.
+struct FusedEdgeAttr {
+  const float* pos = nullptr;   // [N, 2] f32
+  const float* vel = nullptr;   // [N, 2] f32
+  EdgeFeatureSpec spec{};
+  float* edge_attr = nullptr;
+  float* ea_csc = nullptr;
+  int32_t* error_flag = nullptr;
+};
+int csc_build_fused(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, bool counts_ready,
+                    const CscWorkspace& w, int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid, cudaStream_t stream,
+                    const int32_t* node_map, const FusedEdgeAttr& fea);
 
 }  // namespace rgnn

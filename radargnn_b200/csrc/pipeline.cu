@@ -155,21 +155,28 @@ int rgnn_pipeline_forward(const rgnn_pipeline_desc* desc, const float* pos, cons
                                                       desc->r, edge_index, n_edges, workspace, workspace_bytes, stream_));
   }
 
-  // ---- 2. edge attributes ----------------------------------------------------------------
+  // ---- 2 + 3. edge attributes, CSC view, edge attributes in slot order -------------------------
   EdgeFeatureSpec spec;
   RGNN_RETURN_IF_ERROR(make_edge_feature_spec(desc->edge_features, desc->n_edge_features, desc->edge_mode, &spec));
-  RGNN_RETURN_IF_ERROR(launch_edge_features(pos, vel, RGNN_F32, 2, 2, edge_index, n_edges, spec, edge_attr, RGNN_F32,
-                                            error_flag, stream));
-
-  // ---- 3. CSC view + edge attributes in slot order -----------------------------------------
   bool ordered = false;
   for (int l = 0; l < desc->n_layers; ++l)
     if (desc->layers[l].aggr == RGNN_AGGR_ADD || desc->layers[l].aggr == RGNN_AGGR_MEAN) ordered = true;
+  if (!ordered && spec.width > 0) {
+    // max / min only: slot order inside a segment is free, so one pass fills the slots and writes the
+    // attributes in both orders (conv stack in CELL-SORTED node order, see below)
+    FusedEdgeAttr fea;
+    fea.pos = pos; fea.vel = vel; fea.spec = spec; fea.edge_attr = edge_attr; fea.ea_csc = w.ea_csc; fea.error_flag = error_flag;
+    RGNN_RETURN_IF_ERROR(csc_build_fused(edge_index, n_edges, n, counts_ready, w.csc, w.csc_ptr, w.csc_src, w.csc_eid,
+                                         stream, w.graph.rank, fea));
+  } else {
+  RGNN_RETURN_IF_ERROR(launch_edge_features(pos, vel, RGNN_F32, 2, 2, edge_index, n_edges, spec, edge_attr, RGNN_F32,
+                                            error_flag, stream));
   // The conv stack runs in CELL-SORTED node order (node r = original point sorted_idx[r]): spatial
   // neighbours are then neighbours in memory, so the per-edge gathers of B[source] hit L1 / L2.
   RGNN_RETURN_IF_ERROR(csc_build(edge_index, n_edges, n, counts_ready, ordered, w.csc, w.csc_ptr, w.csc_src, w.csc_eid,
                                  stream, w.graph.rank));
   RGNN_RETURN_IF_ERROR(gather_edge_rows(edge_attr, w.csc_eid, n_edges, de, w.ea_csc, stream));
+  }
 
   // ---- 4. conv -> BatchNorm(train) -> ReLU, L times ------------------------------------------
   ConvInput in;
