@@ -192,7 +192,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=self.file, stderr=subprocess.DEVNULL)
+                 "-lms", "20"], stdout=self.file, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
@@ -346,7 +346,6 @@ def main_gpu(args, wl):
     t_e2e = timed(step_host, e2e_steps)
     barrier()
     t_e2e = max_over_ranks(t_e2e)
-    clocks = sampler.stop() if sampler is not None else None
     h2d = int(pos_h.numel() * 4 + vel_h.numel() * 4 + x0_h.numel() * 4)
     d2h = int(h_host.numel() * 4)
 
@@ -356,6 +355,14 @@ def main_gpu(args, wl):
     timed(step_device, args.steps)
     _lib.profile_enable(False)
     totals = _lib.profile_totals()
+    if sampler is not None:
+        # keep the GPU under the same load until nvidia-smi has had time to take a few samples
+        t_end = time.perf_counter() + 0.6
+        while time.perf_counter() < t_end:
+            for _ in range(10):
+                step_device()
+            torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler is not None else None
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
