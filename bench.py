@@ -355,13 +355,12 @@ def main_gpu(args, wl):
     timed(step_device, args.steps)
     _lib.profile_enable(False)
     totals = _lib.profile_totals()
-    if sampler is not None:
-        # keep the GPU under the same load until nvidia-smi has had time to take a few samples
-        t_end = time.perf_counter() + 0.6
-        while time.perf_counter() < t_end:
-            for _ in range(10):
-                step_device()
-            torch.cuda.synchronize()
+    # keep the GPUs under the same load until nvidia-smi has had time to take a few samples (every
+    # rank runs the same number of steps: step_device contains the loss all-reduce)
+    for _ in range(30):
+        for _ in range(10):
+            step_device()
+        torch.cuda.synchronize()
     clocks = sampler.stop() if sampler is not None else None
     peaks = {}
     try:
