@@ -363,3 +363,94 @@ def test_pipeline_config2_10k(ops):
     want = mo.conv_stack_forward(params, torch.from_numpy(x0), torch.from_numpy(E.T.copy()), torch.from_numpy(ef),
                                  4, "MPNNConv", "max", dtype=torch.float64)
     assert mo.relative_error(h.cpu(), want) <= 1e-4
+
+
+def test_pipeline_headline_100k_against_reference_calls(ops):
+    """The headline shape (100 k points, k = 16, 1.6 M edges, 4 x MPNNConv(64 -> 64) + BN + ReLU):
+    edge_index bit-exact against the reference's own sklearn call, edge_attr exact, embeddings within
+    the north star's 1e-4 against the fp32 CPU restatement of the PyG ops."""
+    fr = synthetic.uniform_square(100_000, seed=0)
+    params = _stack_params(4, 64, 64, 2, "MPNNConv", seed=0)
+    x0 = synthetic.node_embeddings(100_000, 64)
+    cfg = _pipeline_cfg(ops, params, 4, "MPNNConv", "max", algorithm="knn", k=16)
+    ei, ea, h = ops.pipeline_forward(cfg, _dev(fr.X_cc, torch.float32), _dev(fr.V_cc_compensated, torch.float32), _dev(x0))
+    E = go.knn_edges_sklearn(fr.X_cc, 16)
+    assert go.kth_gap_is_tie_free(fr.X_cc, E, 16)
+    np.testing.assert_array_equal(ei.cpu().numpy().T, E)
+    ef = go.edge_features(fr.X_cc, fr.V_cc_compensated, E, ["relative_position"], "directed").astype(np.float32)
+    np.testing.assert_array_equal(ea.cpu().numpy(), ef)
+    with torch.no_grad():
+        want = mo.conv_stack_forward(params, torch.from_numpy(x0), torch.from_numpy(E.T.copy()), torch.from_numpy(ef),
+                                     4, "MPNNConv", "max", dtype=torch.float32)
+    assert mo.relative_error(h.cpu(), want) <= 1e-4
+    # run-to-run determinism: the same bytes again
+    ei2, ea2, h2 = ops.pipeline_forward(cfg, _dev(fr.X_cc, torch.float32), _dev(fr.V_cc_compensated, torch.float32), _dev(x0))
+    assert torch.equal(ei, ei2) and torch.equal(ea, ea2) and torch.equal(h, h2)
+
+
+def test_pipeline_config3_shape_batched_frames(ops):
+    """BASELINE config 3 shape: 64 RadarScenes-like frames x 300 points, k = 20, d = 128 (two layers here);
+    P = 258 exceeds the tensor-core tile, so this exercises the fp32 CUDA-core contraction path."""
+    frames = [synthetic.radar_frame(300, seed=s) for s in range(64)]
+    X, V, ptr = synthetic.frame_batch(frames)
+    n = X.shape[0]
+    params = _stack_params(2, 128, 128, 2, "MPNNConv", seed=5)
+    x0 = synthetic.node_embeddings(n, 128, seed=2)
+    cfg = _pipeline_cfg(ops, params, 2, "MPNNConv", "max", algorithm="knn", k=20)
+    ei, ea, h = ops.pipeline_forward(cfg, _dev(X, torch.float32), _dev(V, torch.float32), _dev(x0), ptr)
+    E = go.batched_edges([f.X_cc for f in frames], "knn", k=20, backend="sklearn")
+    np.testing.assert_array_equal(ei.cpu().numpy().T, E)
+    ef = go.edge_features(X, V, E, ["relative_position"], "directed").astype(np.float32)
+    want = mo.conv_stack_forward(params, torch.from_numpy(x0), torch.from_numpy(E.T.copy()), torch.from_numpy(ef),
+                                 2, "MPNNConv", "max", dtype=torch.float64)
+    assert mo.relative_error(h.cpu(), want) <= 1e-4
+
+
+def test_pipeline_config4_shape_point_pair_features(ops):
+    """BASELINE config 4 shape (scaled down): nuScenes-like frames of 2 000 points, k = 20, rotation-invariant
+    point-pair features (De = 4), 4 x MPNNConv(64 -> 64)."""
+    frames = [synthetic.nuscenes_frame(2000, seed=s) for s in range(4)]
+    X, V, ptr = synthetic.frame_batch(frames)
+    n = X.shape[0]
+    params = _stack_params(4, 64, 64, 4, "MPNNConv", seed=6)
+    x0 = synthetic.node_embeddings(n, 64, seed=4)
+    cfg = _pipeline_cfg(ops, params, 4, "MPNNConv", "max", algorithm="knn", k=20, edge_features=["point_pair_features"])
+    ei, ea, h = ops.pipeline_forward(cfg, _dev(X, torch.float32), _dev(V, torch.float32), _dev(x0), ptr)
+    E = go.batched_edges([f.X_cc for f in frames], "knn", k=20, backend="sklearn")
+    np.testing.assert_array_equal(ei.cpu().numpy().T, E)
+    ef = go.edge_features(X, V, E, ["point_pair_features"], "directed").astype(np.float32)
+    np.testing.assert_allclose(ea.cpu().numpy(), ef, rtol=2e-7, atol=2e-5)   # angles: acos rounding, degrees
+    want = mo.conv_stack_forward(params, torch.from_numpy(x0), torch.from_numpy(E.T.copy()), ea.cpu(),
+                                 4, "MPNNConv", "max", dtype=torch.float64)
+    assert mo.relative_error(h.cpu(), want) <= 1e-4
+
+
+def test_tensor_core_path_isolated_nodes_and_weight_cache(ops):
+    """The tcgen05 contraction folds W_m W_t into the update weights; nodes without incoming edge must
+    still get post_mlp([x ; 0]) -- and the cached weight images must follow in-place weight updates."""
+    g = torch.Generator().manual_seed(11)
+    n, e, c = 900, 6000, 64
+    x = torch.randn(n, c, generator=g)
+    ei = torch.randint(0, n // 2, (2, e), generator=g)      # half of the nodes never receive a message
+    ea = torch.randn(e, 2, generator=g)
+    p = 2 * c + 2
+    params = {"pre_mlp.0.weight": torch.randn(p, p, generator=g) / p ** 0.5, "pre_mlp.0.bias": torch.randn(p, generator=g) * 0.1,
+              "post_mlp.0.weight": torch.randn(c, p + c, generator=g) / (p + c) ** 0.5, "post_mlp.0.bias": torch.randn(c, generator=g) * 0.1}
+    dev = {k: v.to(DEV) for k, v in params.items()}
+    cp = ops.ConvParams("MPNNConv", c, c, 2, "max", [(dev["pre_mlp.0.weight"], dev["pre_mlp.0.bias"])],
+                        [(dev["post_mlp.0.weight"], dev["post_mlp.0.bias"])])
+    csc = ops.csc_build(ei.to(DEV), n)
+    got = ops.conv_forward(cp, x.to(DEV), csc, ea.to(DEV)).cpu()
+    want = mo.mpnn_conv_forward(params, x, ei, ea, "max", dtype=torch.float64)
+    assert mo.relative_error(got, want) <= 2e-5
+    isolated = torch.arange(n // 2, n)
+    exact = torch.nn.functional.linear(torch.cat([x[isolated], torch.zeros(len(isolated), p)], 1).double(),
+                                       params["post_mlp.0.weight"].double(), params["post_mlp.0.bias"].double())
+    assert mo.relative_error(got[isolated], exact) <= 2e-5
+    assert cp._packed is not None                                     # the tensor-core images were cached
+    with torch.no_grad():                                             # in-place update bumps the version counter
+        dev["post_mlp.0.weight"].mul_(0.5)
+    params["post_mlp.0.weight"] = params["post_mlp.0.weight"] * 0.5
+    got2 = ops.conv_forward(cp, x.to(DEV), csc, ea.to(DEV)).cpu()
+    want2 = mo.mpnn_conv_forward(params, x, ei, ea, "max", dtype=torch.float64)
+    assert mo.relative_error(got2, want2) <= 2e-5
