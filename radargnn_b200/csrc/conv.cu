@@ -202,6 +202,233 @@ edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, 
   *reinterpret_cast<float4*>(out + node * pp + c0) = r;
 }
 
+// ---- split-layout aggregate (tensor-core path, ConvShape::split) ---------------------------------
+// A QUARTER-WARP (8 lanes) per target node, lane q owns main channels 32 i + 4 q .. + 3 (i = 0..3), so
+// one gather instruction of the warp reads one aligned 128-byte line of four different source rows
+// (4 L1 wavefronts, all bytes used) and the per-slot bookkeeping -- broadcasting the slot's source
+// index and edge attributes with shuffles, the 64-bit address -- is paid once per FOUR rows.  (One thread
+// per (node, 4 channels), the layout above, pays ~8 wavefronts and ~34 instructions per slot plus a
+// strided per-thread weight prologue as expensive as its main loop; a full warp per node pays 3 shuffles
+// per slot per row, and shuffles occupy the same L1 data pipe as the gathers.)  The slot's source index
+// and edge attributes are loaded once per 8 slots (lane = slot) and four slots = 16 gathers per lane are
+// in flight.  The edge term runs on packed FFMA2, max / min on the 3-input FMNMX3.  The p - 128 tail
+// channels live in their own narrow arrays and are processed slot-parallel (lane = slot) with a fixed
+// butterfly over the 8 lanes at the end of the row.  A CTA covers kSplitRows consecutive (cell-sorted)
+// nodes, 16 at a time, so that concurrently gathered sources overlap in L1.
+constexpr int kSplitRows = 64;
+constexpr int kSplitThreads = 128;
+constexpr int kSplitMain = 128;
+
+__device__ __forceinline__ float4 fma4x2(float s, float4 w, float4 a) {
+  const float2 ss = make_float2(s, s);
+  const float2 lo = __ffma2_rn(ss, make_float2(w.x, w.y), make_float2(a.x, a.y));
+  const float2 hi = __ffma2_rn(ss, make_float2(w.z, w.w), make_float2(a.z, a.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+template <int MODE>
+__device__ __forceinline__ float4 combine4(float4 a, float4 b) {
+  if (MODE == RGNN_AGGR_MAX) return max4(a, b);
+  if (MODE == RGNN_AGGR_MIN) return min4(a, b);
+  return add4(a, b);
+}
+// acc (op) v0 (op) v1, in this order (the sums must stay in slot order)
+template <int MODE>
+__device__ __forceinline__ float4 combine4x2(float4 a, float4 v0, float4 v1) {
+  if (MODE == RGNN_AGGR_MAX)
+    return make_float4(fmaxf(fmaxf(a.x, v0.x), v1.x), fmaxf(fmaxf(a.y, v0.y), v1.y), fmaxf(fmaxf(a.z, v0.z), v1.z), fmaxf(fmaxf(a.w, v0.w), v1.w));
+  if (MODE == RGNN_AGGR_MIN)
+    return make_float4(fminf(fminf(a.x, v0.x), v1.x), fminf(fminf(a.y, v0.y), v1.y), fminf(fminf(a.z, v0.z), v1.z), fminf(fminf(a.w, v0.w), v1.w));
+  return add4(add4(a, v0), v1);
+}
+
+template <int MODE, int DE>
+__global__ void __launch_bounds__(kSplitThreads, 3)
+edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restrict__ bt, int p,
+                            const float* __restrict__ bias, const float* __restrict__ w_e, int64_t ldwe,
+                            const float* __restrict__ ea, const int32_t* __restrict__ csc_ptr,
+                            const int32_t* __restrict__ csc_src, int n_nodes, float* __restrict__ out_m,
+                            float* __restrict__ out_t, IsolatedNodeTerm iso) {
+  constexpr int kW = kSplitMain + 4;             // staged channels: main + one float4 of tail
+  __shared__ __align__(16) float ws[DE][kW];     // W_e transposed: ws[d][channel], zero beyond p
+  __shared__ __align__(16) float bs[kW];         // message bias, zero beyond p
+  for (int i = threadIdx.x; i < DE * kW; i += blockDim.x) {
+    const int d = i / kW, ch = i - d * kW;
+    ws[d][ch] = ch < p ? w_e[static_cast<int64_t>(ch) * ldwe + d] : 0.f;
+  }
+  for (int i = threadIdx.x; i < kW; i += blockDim.x) bs[i] = i < p ? bias[i] : 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane & 7, quarter = lane >> 3;
+  float4 w[DE][4], wt[DE];
+#pragma unroll
+  for (int d = 0; d < DE; ++d) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[d][i] = ld4(&ws[d][32 * i + 4 * q]);
+    wt[d] = ld4(&ws[d][kSplitMain]);
+  }
+  constexpr float kInit = MODE == RGNN_AGGR_MAX ? -INFINITY : (MODE == RGNN_AGGR_MIN ? INFINITY : 0.f);
+  const float4 init4 = make_float4(kInit, kInit, kInit, kInit);
+  const float* bcol = bm + 4 * q;
+
+  for (int it = 0; it < kSplitRows / 16; ++it) {
+    const int row = blockIdx.x * kSplitRows + it * 16 + warp * 4 + quarter;
+    const bool live = row < n_nodes;
+    int beg = 0, deg = 0;
+    if (live) { beg = csc_ptr[row]; deg = csc_ptr[row + 1] - beg; }
+    const int nmax = __reduce_max_sync(0xffffffffu, deg);
+    float4 acc[4] = {init4, init4, init4, init4};
+    float4 tacc = init4;
+    for (int b = 0; b < nmax; b += 8) {
+      // lane q of the quarter holds slot b + q of its row
+      int my_src = 0;
+      float my_e[DE];
+#pragma unroll
+      for (int d = 0; d < DE; ++d) my_e[d] = 0.f;
+      if (b + q < deg) {
+        const int slot = beg + b + q;
+        my_src = csc_src[slot];
+        const float* e = ea + static_cast<int64_t>(slot) * DE;
+#pragma unroll
+        for (int d = 0; d < DE; ++d) my_e[d] = e[d];
+        float4 t = ld4(bt + static_cast<int64_t>(my_src) * 4);
+#pragma unroll
+        for (int d = 0; d < DE; ++d) t = fma4(my_e[d], wt[d], t);
+        tacc = combine4<MODE>(tacc, t);
+      }
+#pragma unroll
+      for (int j0 = 0; j0 < 8; j0 += 4) {
+        if (b + j0 < nmax) {   // warp-uniform
+          float4 v[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int sidx = __shfl_sync(0xffffffffu, my_src, j0 + u, 8);
+            const bool on = b + j0 + u < deg;
+            const float* rp = bcol + static_cast<int64_t>(sidx) * kSplitMain;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[u][i] = on ? ld4(rp + 32 * i) : init4;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int d = 0; d < DE; ++d) {
+              const float ed = __shfl_sync(0xffffffffu, my_e[d], j0 + u, 8);   // 0 for slots beyond the row's degree
+#pragma unroll
+              for (int i = 0; i < 4; ++i) v[u][i] = fma4x2(ed, w[d][i], v[u][i]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[i] = combine4x2<MODE>(acc[i], v[0][i], v[1][i]);
+            acc[i] = combine4x2<MODE>(acc[i], v[2][i], v[3][i]);
+          }
+        }
+      }
+    }
+    // tail: fixed-order butterfly over the quarter's 8 lanes (= slots)
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      float4 other = tacc;
+      other.x = __shfl_xor_sync(0xffffffffu, tacc.x, o);
+      if (DE > 1) other.y = __shfl_xor_sync(0xffffffffu, tacc.y, o);
+      if (DE > 2) other.z = __shfl_xor_sync(0xffffffffu, tacc.z, o);
+      if (DE > 3) other.w = __shfl_xor_sync(0xffffffffu, tacc.w, o);
+      tacc = combine4<MODE>(tacc, other);
+    }
+    if (!live) continue;
+    float4 bmain[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bmain[i] = ld4(&bs[32 * i + 4 * q]);
+    const float4 btail = ld4(&bs[kSplitMain]);
+    float4 r[4], rt = make_float4(0.f, 0.f, 0.f, 0.f);  // torch_scatter: empty segments aggregate to 0
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = rt;
+    if (deg > 0) {
+      if (MODE == RGNN_AGGR_MAX || MODE == RGNN_AGGR_MIN) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = add4(bmain[i], acc[i]);
+        rt = add4(btail, tacc);
+      } else if (MODE == RGNN_AGGR_ADD) {
+        const float fd = static_cast<float>(deg);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = fma4(fd, bmain[i], acc[i]);
+        rt = fma4(fd, btail, tacc);
+      } else {
+        const float inv = 1.f / static_cast<float>(deg);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = fma4(inv, acc[i], bmain[i]);
+        rt = fma4(inv, tacc, btail);
+      }
+    } else if (iso.w_t != nullptr) {
+      // Folded formulation (node_gemm.cu): the update weights carry W_m W_t for every node, so a node
+      // without incoming edge cancels that term with M' = -W_t x_n instead of 0 (rare: strided reads)
+      float a16[4][4], t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a16[i][j] = 0.f;
+      const float* xr = iso.x + (iso.rows != nullptr ? static_cast<int64_t>(iso.rows[row]) : row) * iso.ldx;
+      for (int c = 0; c < iso.c; ++c) {
+        float xv = xr[c];
+        if (iso.mean != nullptr) xv = (xv - iso.mean[c]) * iso.scale[c] + iso.beta[c];
+        if (iso.relu) xv = fmaxf(xv, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            a16[i][j] = fmaf(iso.w_t[static_cast<int64_t>(32 * i + 4 * q + j) * iso.ldw + c], xv, a16[i][j]);
+        if (q == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (kSplitMain + j < p) t4[j] = fmaf(iso.w_t[static_cast<int64_t>(kSplitMain + j) * iso.ldw + c], xv, t4[j]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = make_float4(-a16[i][0], -a16[i][1], -a16[i][2], -a16[i][3]);
+      rt = make_float4(-t4[0], -t4[1], -t4[2], -t4[3]);
+    }
+    float* orow = out_m + static_cast<int64_t>(row) * kSplitMain + 4 * q;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(orow + 32 * i) = r[i];
+    if (q == 0) *reinterpret_cast<float4*>(out_t + static_cast<int64_t>(row) * 4) = rt;
+  }
+}
+
+template <int MODE>
+int launch_edge_aggregate_split_mode(const float* bm, const float* bt, const ConvShape& s, const float* bias,
+                                     const float* w_e, int64_t ldwe, const float* ea, const int32_t* csc_ptr,
+                                     const int32_t* csc_src, int64_t n_nodes, float* out_m, float* out_t,
+                                     cudaStream_t stream, const IsolatedNodeTerm& iso) {
+  const unsigned blocks = div_up(n_nodes, kSplitRows);
+  const int n = static_cast<int>(n_nodes);
+#define RGNN_SPLIT_CASE(DE_)                                                                                   \
+  case DE_:                                                                                                    \
+    edge_aggregate_split_kernel<MODE, DE_><<<blocks, kSplitThreads, 0, stream>>>(bm, bt, s.p, bias, w_e, ldwe, ea, csc_ptr, \
+                                                                        csc_src, n, out_m, out_t, iso);       \
+    break;
+  switch (s.de) {
+    RGNN_SPLIT_CASE(1) RGNN_SPLIT_CASE(2) RGNN_SPLIT_CASE(3) RGNN_SPLIT_CASE(4)
+    default: return RGNN_ERR_UNSUPPORTED;
+  }
+#undef RGNN_SPLIT_CASE
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
+}
+
+int launch_edge_aggregate_split(int aggr, const float* bm, const float* bt, const ConvShape& s, const float* bias,
+                                const float* w_e, int64_t ldwe, const float* ea, const int32_t* csc_ptr,
+                                const int32_t* csc_src, int64_t n_nodes, float* out_m, float* out_t,
+                                cudaStream_t stream, const IsolatedNodeTerm& iso) {
+  RGNN_PROFILE("edge_aggregate", stream);
+  if (s.pm != kSplitMain || s.pt4 != 4) return RGNN_ERR_UNSUPPORTED;
+  switch (aggr) {
+    case RGNN_AGGR_MAX: return launch_edge_aggregate_split_mode<RGNN_AGGR_MAX>(bm, bt, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, out_m, out_t, stream, iso);
+    case RGNN_AGGR_MIN: return launch_edge_aggregate_split_mode<RGNN_AGGR_MIN>(bm, bt, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, out_m, out_t, stream, iso);
+    case RGNN_AGGR_ADD: return launch_edge_aggregate_split_mode<RGNN_AGGR_ADD>(bm, bt, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, out_m, out_t, stream, iso);
+    default: return launch_edge_aggregate_split_mode<RGNN_AGGR_MEAN>(bm, bt, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, out_m, out_t, stream, iso);
+  }
+}
+
 // general path: M[n] = reduce over the node's slots of U[slot] (already through pre_mlp)
 template <int MODE>
 __global__ void __launch_bounds__(kAggThreads)
@@ -318,19 +545,28 @@ static int pack_conv_weights(const rgnn_conv_desc& d, const ConvShape& s, float*
   wb.block[0] = {d.pre_weight[0] + x_s_off, s.p, s.p, s.c, 0, 0};
   RGNN_RETURN_IF_ERROR(tc_pack_weights(wb, conv_pre_shape(s), wpack_pre, stream));
   const int64_t ldpost = s.c + s.p;
-  wb.count = 2;
-  wb.block[0] = {d.post_weight[0], ldpost, s.c_out, s.c, 0, 0};
-  wb.block[1] = {d.post_weight[0] + s.c, ldpost, s.c_out, s.p, tc_seg_pad(s.c), 0};  // segments start on 32-float chunks
+  int nb = 0;
+  wb.block[nb++] = {d.post_weight[0], ldpost, s.c_out, s.c, 0, 0};
+  int k_off = tc_seg_pad(s.c);  // segments start on 32-float panels
+  if (s.split) {
+    wb.block[nb++] = {d.post_weight[0] + s.c, ldpost, s.c_out, s.pm, k_off, 0};
+    k_off += tc_seg_pad(s.pm);
+    wb.block[nb++] = {d.post_weight[0] + s.c + s.pm, ldpost, s.c_out, s.p - s.pm, k_off, 0};
+    k_off += tc_seg_pad(s.pt4);
+  } else {
+    wb.block[nb++] = {d.post_weight[0] + s.c, ldpost, s.c_out, s.p, k_off, 0};
+    k_off += tc_seg_pad(s.pp);
+  }
   if (mpnn) {
     RGNN_RETURN_IF_ERROR(tc_fold_weights(d.post_weight[0] + s.c, ldpost, d.pre_weight[0], s.p, s.c_out, s.p, s.c,
                                          w_fold, stream));
-    wb.count = 3;
     if (d.aggr == RGNN_AGGR_ADD) {
-      wb.block[2] = {w_fold, s.c, s.c_out, s.c, tc_seg_pad(s.c) + tc_seg_pad(s.pp), 0};   // deg * x segment
+      wb.block[nb++] = {w_fold, s.c, s.c_out, s.c, k_off, 0};   // deg * x segment
     } else {
-      wb.block[2] = {w_fold, s.c, s.c_out, s.c, 0, 1};            // added onto W_x: (W_x + W_m W_t) x
+      wb.block[nb++] = {w_fold, s.c, s.c_out, s.c, 0, 1};       // added onto W_x: (W_x + W_m W_t) x
     }
   }
+  wb.count = nb;
   return tc_pack_weights(wb, conv_post_shape(d, s), wpack_post, stream);
 }
 
@@ -355,6 +591,18 @@ int conv_shape(const rgnn_conv_desc& d, ConvShape* s) {
   }
   s->pp = (s->p + 3) & ~3;
   s->general = d.pre_layers > 1;
+  s->split = false; s->pm = 0; s->pt4 = 0;
+  {
+    // split message layout: main part = the node-feature columns of the message (2C or C), tail = the
+    // edge-attribute columns; taken when the main rows are exactly one float4 per lane of a warp, the
+    // edge weights fit the aggregate kernel's registers and both contractions run on the tensor cores
+    const int main_cols = s->p - s->de_eff;
+    if (!s->general && !d.use_edge_encoder && main_cols == 128 && s->de >= 1 && s->de <= 4) {
+      ConvShape t = *s;
+      t.split = true; t.pm = main_cols; t.pt4 = (s->p - main_cols + 3) & ~3;
+      if (tc_gemm_supported(conv_pre_shape(t)) && tc_gemm_supported(conv_post_shape(d, t))) *s = t;
+    }
+  }
   for (int l = 0; l < d.pre_layers; ++l)
     if (d.pre_weight[l] == nullptr || d.pre_bias[l] == nullptr) return RGNN_ERR_INVALID_ARGUMENT;
   for (int l = 0; l < d.post_layers; ++l)
@@ -404,6 +652,7 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
   // ---- tensor-core path: B = x W_s^T, fold W_t through the update, fused BN column sums ---------
   const bool aligned = (in.ldx % 4 == 0) && (reinterpret_cast<uintptr_t>(in.x) % 16 == 0) &&
                        (in.mean == nullptr || reinterpret_cast<uintptr_t>(in.mean) % 16 == 0);
+  if (s.split && !(w.tc_post && aligned)) return RGNN_ERR_UNSUPPORTED;  // split buffers only fit the tensor-core path
   if (w.tc_post && aligned) {
     // weight images: the caller's pre-packed buffer, or (weights may have changed since the last call)
     // repacked into the workspace on every forward
@@ -425,6 +674,7 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
     g1.a1_mean = in.mean; g1.a1_scale = in.scale; g1.a1_beta = in.beta; g1.relu_a1 = in.relu;
     g1.wpack = wpack_pre; g1.n = s.p; g1.n_store = s.pp;
     g1.y = w.b; g1.ldy = s.pp; g1.m = n_nodes; g1.status = w.tc_status;
+    if (s.split) { g1.ldy = s.pm; g1.y2 = w.bt; g1.ldy2 = s.pt4; g1.n_split = s.pm; g1.n_store = s.pm + s.pt4; }
     RGNN_RETURN_IF_ERROR(launch_tc_gemm(g1, "node_gemm_pre", stream));
 
     // M'_n = b + max_e (...) (mean: b + mean; add: deg b + sum): the W_t x_t term is folded into the
@@ -435,6 +685,10 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
       iso.w_t = d.pre_weight[0]; iso.ldw = s.p; iso.x = in.x; iso.ldx = in.ldx; iso.c = s.c; iso.rows = in.rows;
       iso.mean = in.mean; iso.scale = in.scale; iso.beta = in.beta; iso.relu = in.relu;
     }
+    if (s.split) {
+      RGNN_RETURN_IF_ERROR(launch_edge_aggregate_split(d.aggr, w.b, w.bt, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes,
+                                                       w.m, w.mt, stream, iso));
+    } else
     switch (d.aggr) {
       case RGNN_AGGR_MAX: RGNN_RETURN_IF_ERROR(launch_edge_aggregate<RGNN_AGGR_MAX>(nullptr, w.b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, w.m, stream, iso)); break;
       case RGNN_AGGR_MIN: RGNN_RETURN_IF_ERROR(launch_edge_aggregate<RGNN_AGGR_MIN>(nullptr, w.b, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes, w.m, stream, iso)); break;
@@ -447,6 +701,7 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
     g2.a1 = in.x; g2.lda1 = in.ldx; g2.k1 = s.c; g2.a1_rows = in.rows;
     g2.a1_mean = in.mean; g2.a1_scale = in.scale; g2.a1_beta = in.beta; g2.relu_a1 = in.relu;
     g2.a2 = w.m; g2.lda2 = s.pp; g2.k2 = s.pp;
+    if (s.split) { g2.lda2 = s.pm; g2.k2 = s.pm; g2.at = w.mt; g2.ldat = s.pt4; g2.kt = s.pt4; }
     if (third_segment) { g2.k3 = s.c; g2.csc_ptr = csc_ptr; g2.rowscale_mode = 2; }
     g2.wpack = wpack_post; g2.n = s.c_out; g2.n_store = s.c_out; g2.bias = d.post_bias[0];
     g2.y = first_out; g2.ldy = s.c_out; g2.m = n_nodes; g2.status = w.tc_status;

@@ -21,12 +21,20 @@ struct ConvInput {
 struct ConvShape {
   int32_t c, c_out, de, de_eff, p, pp;  // pp = p rounded up to a multiple of 4 (16-byte rows)
   bool general;                          // pre_layers > 1: per-edge MLP cannot be factored
+  // Split message layout (tensor-core path only): the message rows B / M' are kept as a main array
+  // [N, pm] whose rows are whole 128-byte lines (pm = 128: one float4 per lane of a warp) plus a narrow
+  // tail array [N, pt4] for the remaining p - pm channels, so that the per-edge gathers are aligned
+  // 512-byte row reads.  split == false: one [N, pp] array.
+  bool split;
+  int32_t pm, pt4;
 };
 
 struct ConvWorkspace {
   float* a;        // [N, pp]  x W_t^T  (MPNN only)
-  float* b;        // [N, pp]  x W_s^T
-  float* m;        // [N, pp]  aggregated messages
+  float* b;        // [N, pp]  x W_s^T            (split layout: [N, pm])
+  float* m;        // [N, pp]  aggregated messages (split layout: [N, pm])
+  float* bt;       // [N, pt4] tail channels of B  (split layout only)
+  float* mt;       // [N, pt4] tail channels of M
   float* t1;       // [N, c_out] post_mlp ping-pong (post_layers > 1)
   float* t2;
   float* w_eff;    // [p, de] folded edge-encoder weight
@@ -46,7 +54,7 @@ struct ConvWorkspace {
 // shapes of the two node contractions of a layer when they run on the tensor cores
 inline TcGemmShape conv_pre_shape(const ConvShape& s) { TcGemmShape t; t.k1 = s.c; t.n = s.p; return t; }
 inline TcGemmShape conv_post_shape(const rgnn_conv_desc& d, const ConvShape& s) {
-  TcGemmShape t; t.k1 = s.c; t.k2 = s.pp;
+  TcGemmShape t; t.k1 = s.c; t.k2 = s.split ? s.pm : s.pp; t.kt = s.split ? s.pt4 : 0;
   t.k3 = (d.conv_type == RGNN_CONV_MPNN && d.aggr == RGNN_AGGR_ADD) ? s.c : 0;  // deg * x only for add
   t.n = s.c_out; return t;
 }
@@ -57,10 +65,14 @@ template <typename ArenaT>
 inline ConvWorkspace carve_conv_workspace(ArenaT& a, const rgnn_conv_desc& d, const ConvShape& s,
                                           int64_t n_nodes, int64_t n_edges, bool need_ea_gather) {
   ConvWorkspace w{};
-  const size_t npp = static_cast<size_t>(n_nodes) * s.pp;
-  w.a = d.conv_type == RGNN_CONV_MPNN ? a.template take<float>(npp) : nullptr;  // unused on the tensor-core path
+  const size_t npp = static_cast<size_t>(n_nodes) * (s.split ? s.pm : s.pp);
+  w.a = (d.conv_type == RGNN_CONV_MPNN && !s.split) ? a.template take<float>(npp) : nullptr;  // unused on the tensor-core path
   w.b = a.template take<float>(npp);
   w.m = a.template take<float>(npp);
+  if (s.split) {
+    w.bt = a.template take<float>(static_cast<size_t>(n_nodes) * s.pt4);
+    w.mt = a.template take<float>(static_cast<size_t>(n_nodes) * s.pt4);
+  }
   if (d.post_layers > 1) {
     w.t1 = a.template take<float>(static_cast<size_t>(n_nodes) * s.c_out);
     w.t2 = a.template take<float>(static_cast<size_t>(n_nodes) * s.c_out);

@@ -29,7 +29,6 @@ namespace {
 
 constexpr int kRows = 128;     // UMMA M
 constexpr int kKc = 32;        // floats of K per chunk (4 MMA k-steps of 8)
-constexpr int kThreads = 256;
 constexpr int kABufFloats = kRows * kKc;  // one hi or lo image of a chunk
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -170,33 +169,51 @@ fold_weights_kernel(const float* __restrict__ w_m, int64_t ld_m, const float* __
 }
 
 // ---- the GEMM ------------------------------------------------------------------------------
-// Warp roles (800 threads, one CTA per SM, persistent over 128-row tiles):
-//   warps 0-15  producers: cp.async raw K chunks, transform + hi/lo split, write the swizzled A stages
-//   warps 16-23 epilogue:  TMEM -> registers -> global (+ BatchNorm column sums); two warps per TMEM lane
+// K is laid out segment by segment, [a1 | a2 | a_tail | rowscale * a1], each padded to whole panels of
+// 32 floats (one 128-byte swizzled column block), so a panel lies in exactly one segment.
+//
+// Warp roles (544 threads, one CTA per SM, persistent over 128-row tiles):
+//   warps 0-7   producers: one panel (128 rows x 32 floats) per barrier round.  Each thread loads its four
+//               16-byte items of the NEXT panel straight into registers (coalesced LDG.128, 8 threads per
+//               128-byte row segment) before it transforms (BatchNorm + ReLU on load, row scale), splits
+//               and stores the current one into the swizzled hi / lo stage -- the global latency of panel
+//               g + 1 hides behind the round of panel g; no staging ring, ~60 instructions per round.
+//   warps 8-15  epilogue:  TMEM -> registers -> global (+ BatchNorm column sums); two warps per TMEM lane
 //               quarter, alternating 16-column blocks
-//   warp  24    MMA issuer (one lane): tcgen05.mma per 8-float k-step, tcgen05.commit to the barriers
-// Every role is latency-bound per warp (short dependent chains between barriers), hence many warps.
+//   warp  16    MMA issuer (one lane): tcgen05.mma per 8-float k-step, tcgen05.commit to the barriers
 // Hand-offs are mbarriers only: full[s] (producers -> MMA), empty[s] (MMA done -> producers),
-// acc_full[a] (MMA -> epilogue), acc_empty[a] (epilogue -> MMA).  Two A stages and two TMEM
+// acc_full[a] (MMA -> epilogue), acc_empty[a] (epilogue -> MMA).  Up to three A stages and two TMEM
 // accumulators, so loads, conversion, MMAs and the epilogue of consecutive tiles overlap.
-constexpr int kRing = 2;             // raw K-chunk slots (cp.async targets), 16 KB each
-constexpr int kProducerWarps = 16;
+constexpr int kMaxStages = 3;
+constexpr int kProducerWarps = 8;
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpilogueThreads = 256;
-constexpr int kItems = 1024 / kProducerThreads;   // float4 items of a chunk per producer thread
+constexpr int kItems = 1024 / kProducerThreads;   // float4 items of a panel per producer thread
 constexpr int kGemmThreads = kProducerThreads + kEpilogueThreads + 32;
 constexpr int kMmaWarp = (kProducerThreads + kEpilogueThreads) / 32;
+constexpr int kMaxPanels = 16;
+
+enum PanelFlags : int32_t { kPanelBn = 1, kPanelRelu = 2, kPanelRowScale = 4, kPanelGather = 8 };
+
+struct PanelInfo {
+  const float* base;   // segment base pointer (column 0 of the segment)
+  int64_t ld;          // row stride of the segment, floats
+  int32_t col0;        // first segment column of this panel
+  int32_t valid;       // valid floats in this panel (multiple of 4, <= 32)
+  int32_t flags;
+  int32_t ksteps;      // 8-float MMA k-steps that carry data
+};
 
 struct SmemLayout {
   float* w_hi; float* w_lo;
-  float* a_hi[2]; float* a_lo[2];  // converted chunks (hi / lo images), 1 or 2 stages
-  float* raw;                      // [kRing][128 x 32] chunks as loaded (same swizzled layout)
+  float* a_base;                   // converted panels: stage i = hi image at a_base + i * 2 * kABufFloats, lo image after it
   float* col_sum;                  // [2 accumulators][4 quarters][np]
   float* col_sq;
   float* bias;                     // [np]
   float* bn;                       // [3][k1] mean | scale | beta of the a1 transform
   float* stage;                    // optional: 8 epilogue warps x [32][36] transpose buffers (coalesced stores)
-  uint64_t* bar;                   // full[2], empty[2], acc_full[2], acc_empty[2]
+  PanelInfo* panel;                // [kMaxPanels]
+  uint64_t* bar;                   // full[3], empty[3], acc_full[2], acc_empty[2]
   uint32_t* tmem_base;
 };
 
@@ -207,21 +224,15 @@ __device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int np, in
   float* f = reinterpret_cast<float*>(base);
   s.w_hi = f; f += static_cast<size_t>(np) * kp32;
   s.w_lo = f; f += static_cast<size_t>(np) * kp32;
-  s.a_hi[0] = f; f += kABufFloats;
-  s.a_lo[0] = f; f += kABufFloats;
-  s.a_hi[1] = s.a_hi[0]; s.a_lo[1] = s.a_lo[0];
-  if (a_stages == 2) {
-    s.a_hi[1] = f; f += kABufFloats;
-    s.a_lo[1] = f; f += kABufFloats;
-  }
-  s.raw = f; f += kRing * kABufFloats;
+  s.a_base = f; f += static_cast<size_t>(a_stages) * 2 * kABufFloats;
   s.col_sum = f; f += 8 * np;
   s.col_sq = f; f += 8 * np;
   s.bias = f; f += np;
-  s.bn = f; f += 3 * k1;
+  s.bn = f; f += 3 * ((k1 + 3) & ~3);
   s.stage = nullptr;
   if (staged) { s.stage = f; f += kStageFloats; }
-  s.bar = reinterpret_cast<uint64_t*>(f); f += 16;
+  s.panel = reinterpret_cast<PanelInfo*>(f); f += kMaxPanels * (sizeof(PanelInfo) / sizeof(float));
+  s.bar = reinterpret_cast<uint64_t*>(f); f += 24;
   s.tmem_base = reinterpret_cast<uint32_t*>(f);
   return s;
 }
@@ -234,6 +245,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 node_gemm_kernel(TcGemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -243,15 +261,14 @@ node_gemm_kernel(TcGemmParams p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int acc_cols = 2 * np;
   const int tmem_cols = acc_cols <= 32 ? 32 : (acc_cols <= 64 ? 64 : (acc_cols <= 128 ? 128 : (acc_cols <= 256 ? 256 : 512)));
-  uint64_t* full = s.bar;           // [2]
-  uint64_t* empty = s.bar + 2;      // [2]
-  uint64_t* acc_full = s.bar + 4;   // [2]
-  uint64_t* acc_empty = s.bar + 6;  // [2]
+  uint64_t* full = s.bar;            // [3]
+  uint64_t* empty = s.bar + 3;       // [3]
+  uint64_t* acc_full = s.bar + 6;    // [2]
+  uint64_t* acc_empty = s.bar + 8;   // [2]
 
   // ---- one-time setup: barriers, TMEM, resident weights, bias, BatchNorm-on-load parameters ------
   if (tid == 0) {
-    mbar_init(&full[0], kProducerThreads); mbar_init(&full[1], kProducerThreads);
-    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+    for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], kProducerThreads); mbar_init(&empty[i], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_init(&acc_empty[0], kEpilogueThreads); mbar_init(&acc_empty[1], kEpilogueThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -260,6 +277,8 @@ node_gemm_kernel(TcGemmParams p) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s.tmem_base)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  const int k1p = (p.k1 + 31) & ~31, k2p = (p.k2 + 31) & ~31, ktp = (p.kt + 31) & ~31;
+  const int chunks_per_tile = (kp + kKc - 1) / kKc;
   {
     // resident weights: fire-and-forget cp.async (no register staging), waited for before the barrier
     const int total16 = (2 * np * kp32) >> 2;
@@ -268,9 +287,31 @@ node_gemm_kernel(TcGemmParams p) {
     asm volatile("cp.async.commit_group;" ::: "memory");
     for (int i = tid; i < np; i += kGemmThreads) s.bias[i] = (p.bias != nullptr && i < p.n) ? p.bias[i] : 0.f;
     if (p.a1_mean != nullptr) {
+      const int k1r = (p.k1 + 3) & ~3;
       for (int i = tid; i < p.k1; i += kGemmThreads) {
-        s.bn[i] = p.a1_mean[i]; s.bn[p.k1 + i] = p.a1_scale[i]; s.bn[2 * p.k1 + i] = p.a1_beta[i];
+        s.bn[i] = p.a1_mean[i]; s.bn[k1r + i] = p.a1_scale[i]; s.bn[2 * k1r + i] = p.a1_beta[i];
       }
+    }
+    if (tid < chunks_per_tile && tid < kMaxPanels) {
+      // which segment panel `tid` lies in
+      const int k0 = tid * kKc;
+      PanelInfo pi;
+      const int a1_flags = (p.a1_mean != nullptr ? kPanelBn : 0) | (p.relu_a1 ? kPanelRelu : 0) |
+                           (p.a1_rows != nullptr ? kPanelGather : 0);
+      if (k0 < k1p) {
+        pi.base = p.a1; pi.ld = p.lda1; pi.col0 = k0; pi.valid = min(32, p.k1 - k0); pi.flags = a1_flags;
+      } else if (k0 < k1p + k2p) {
+        pi.base = p.a2; pi.ld = p.lda2; pi.col0 = k0 - k1p; pi.valid = min(32, p.k2 - pi.col0);
+        pi.flags = p.relu_a2 ? kPanelRelu : 0;
+      } else if (k0 < k1p + k2p + ktp) {
+        pi.base = p.at; pi.ld = p.ldat; pi.col0 = k0 - k1p - k2p; pi.valid = min(32, p.kt - pi.col0);
+        pi.flags = p.relu_a2 ? kPanelRelu : 0;
+      } else {
+        pi.base = p.a1; pi.ld = p.lda1; pi.col0 = k0 - k1p - k2p - ktp; pi.valid = min(32, p.k3 - pi.col0);
+        pi.flags = a1_flags | kPanelRowScale;
+      }
+      pi.ksteps = (pi.valid + 7) >> 3;
+      s.panel[tid] = pi;
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
   }
@@ -280,7 +321,6 @@ node_gemm_kernel(TcGemmParams p) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *s.tmem_base;
 
-  const int chunks_per_tile = (kp + kKc - 1) / kKc;
   const int64_t n_tiles = (p.m + kRows - 1) / kRows;
   const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   bool timed_out = false;
@@ -290,65 +330,34 @@ node_gemm_kernel(TcGemmParams p) {
 
   if (warp < kProducerWarps) {
     // =========================== producers ===========================
-    // K is laid out segment by segment, each padded to whole 32-float chunks, so a chunk lies in
-    // exactly one segment: the segment logic is decided once per chunk, not per element.
-    const int k1p = (p.k1 + 31) & ~31, k2p = (p.k2 + 31) & ~31;
-    const int r8 = lane & 7, kq = lane >> 3;
-    const uint32_t raw_addr = smem_u32(s.raw);
-    const bool has_bn = p.a1_mean != nullptr;
+    // thread -> (16-byte chunk c of the 128-byte row segment, rows r0 + 32 i): eight consecutive threads
+    // read one contiguous 128-byte row segment and write one swizzled 128-byte stage row
+    const int c = tid & 7, r0 = tid >> 3;
+    const int off0 = (r0 >> 3) * 256 + (r0 & 7) * 32 + ((c ^ (r0 & 7)) << 2);
     const int m32 = static_cast<int>(p.m);
-    // chunk-invariant coordinates of this thread's items
-    int rloc[kItems], kcol[kItems], off[kItems];
+    const int k1r = (p.k1 + 3) & ~3;
+    const int64_t total = my_tiles * chunks_per_tile;
+
+    auto load_panel = [&](int64_t tl, int pi, float4 (&v)[kItems]) {
+      const PanelInfo& info = s.panel[pi];
+      const int row0 = static_cast<int>(blockIdx.x + tl * gridDim.x) * kRows + r0;
+      const bool col_ok = 4 * c < info.valid;
+      const float* colp = info.base + info.col0 + 4 * c;
+      const bool gather = (info.flags & kPanelGather) != 0;
 #pragma unroll
-    for (int it = 0; it < kItems; ++it) {
-      const int u = it * kProducerWarps + warp;
-      const int k4 = ((u & 1) << 2) + kq;
-      rloc[it] = (u >> 1) * 8 + r8;
-      kcol[it] = k4 * 4;
-      off[it] = (u >> 1) * 256 + r8 * 32 + ((k4 ^ r8) << 2);
-    }
-    // ---- prefetch stream (runs up to two chunks ahead, possibly already in the next tile) --------
-    int64_t pf_tl = 0;
-    int pf_kc = 0, pf_slot = 0;
-    const float* pf_a1[kItems];
-    const float* pf_a2[kItems];
-    bool pf_ok[kItems];
-    auto prefetch = [&]() {
-      if (pf_tl < my_tiles) {
-        if (pf_kc == 0) {
-          const int row0 = static_cast<int>(blockIdx.x + pf_tl * gridDim.x) * kRows;
-#pragma unroll
-          for (int it = 0; it < kItems; ++it) {
-            const int row = row0 + rloc[it];
-            pf_ok[it] = row < m32;
-            const int rr = pf_ok[it] ? row : 0;
-            const int64_t arow = p.a1_rows != nullptr ? p.a1_rows[rr] : rr;
-            pf_a1[it] = p.a1 + arow * p.lda1 + kcol[it];
-            pf_a2[it] = p.a2 != nullptr ? p.a2 + static_cast<int64_t>(rr) * p.lda2 + kcol[it] : p.a1;
-          }
+      for (int it = 0; it < kItems; ++it) {
+        const int row = row0 + 32 * it;
+        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && row < m32) {
+          const int64_t rr = gather ? static_cast<int64_t>(p.a1_rows[row]) : static_cast<int64_t>(row);
+          v[it] = ldg_f4(colp + rr * info.ld);
         }
-        const int k0 = pf_kc * kKc;
-        const uint32_t slot_addr = raw_addr + static_cast<uint32_t>(pf_slot) * (kABufFloats * 4u);
-        const bool seg1 = k0 >= k1p && k0 < k1p + k2p;
-        const int col0 = k0 < k1p ? k0 : (seg1 ? k0 - k1p : k0 - k1p - k2p);
-        const int seg_len = seg1 ? p.k2 : p.k1;
-#pragma unroll
-        for (int it = 0; it < kItems; ++it) {
-          const bool valid = pf_ok[it] && (col0 + kcol[it] < seg_len);
-          const float* src = (seg1 ? pf_a2[it] : pf_a1[it]) + col0;
-          cp_async16(slot_addr + off[it] * 4u, valid ? src : p.a1, valid ? 16u : 0u);
-        }
-        if (++pf_kc == chunks_per_tile) { pf_kc = 0; ++pf_tl; }
-        pf_slot ^= 1;
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");  // always commit: uniform group accounting
     };
-    // L2 prefetch of a whole tile's A rows, one tile ahead of the cp.async stream: the ring only holds
-    // 32 KB per SM, too little to cover DRAM latency at full bandwidth, but enough for L2 latency.
+    // L2 prefetch of a whole tile's A rows, two tiles ahead of the register stream
     const int lines1 = (p.k1 * 4 + 127) >> 7, lines2 = (p.k2 * 4 + 127) >> 7;
     auto l2_prefetch_tile = [&](int64_t tl) {
       if (tl >= my_tiles) return;
-      if (tid >= 256) return;
       const int row = static_cast<int>(blockIdx.x + tl * gridDim.x) * kRows + (tid & 127);
       if (row >= m32) return;
       const int64_t arow = p.a1_rows != nullptr ? p.a1_rows[row] : row;
@@ -358,111 +367,116 @@ node_gemm_kernel(TcGemmParams p) {
         const float* addr = l < lines1 ? r1 + l * 32 : r2 + (l - lines1) * 32;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
       }
+      if (p.at != nullptr && (tid >> 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.at + static_cast<int64_t>(row) * p.ldat));
     };
-    l2_prefetch_tile(0);
     l2_prefetch_tile(1);
-    prefetch();
-    prefetch();
-    uint32_t g = 0;  // chunk counter of the convert stream
-    for (int64_t tl = 0; tl < my_tiles; ++tl) {
-      if (trace != nullptr && tid == 0 && tl < 32) trace[0 * 64 + tl * 2] = clock64();
-      l2_prefetch_tile(tl + 2);
-      const int row0 = static_cast<int>(blockIdx.x + tl * gridDim.x) * kRows;
-      bool ok[kItems];
-      float rs[kItems];
+
+    float4 cur[kItems], nxt[kItems];
+    int64_t ld_tl = 0; int ld_pi = 0;      // next panel to load
+    if (total > 0) {
+      load_panel(0, 0, cur);
+      if (++ld_pi == chunks_per_tile) { ld_pi = 0; ++ld_tl; }
+    }
+    int stg = 0;            // stage of panel g
+    uint32_t round = 0;     // how often the stage ring has wrapped
+    int64_t tl = 0; int pi = 0;
+    for (int64_t g = 0; g < total; ++g) {
+      if (pi == 0) {
+        if (trace != nullptr && tid == 0 && tl < 32) trace[0 * 64 + tl * 2] = clock64();
+        l2_prefetch_tile(tl + 2);
+      }
+      if (ld_tl < my_tiles) {
+        load_panel(ld_tl, ld_pi, nxt);
+        if (++ld_pi == chunks_per_tile) { ld_pi = 0; ++ld_tl; }
+      }
+      // ---- transform + split the current panel ------------------------------------------------
+      const PanelInfo& info = s.panel[pi];
+      const int flags = info.flags;
+      const int colc = info.col0 + 4 * c;
+      const bool col_ok = 4 * c < info.valid;
+      const int row0 = static_cast<int>(blockIdx.x + tl * gridDim.x) * kRows + r0;
+      float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), be = mu;
+      if ((flags & kPanelBn) && col_ok) {
+        mu = *reinterpret_cast<const float4*>(s.bn + colc);
+        sc = *reinterpret_cast<const float4*>(s.bn + k1r + colc);
+        be = *reinterpret_cast<const float4*>(s.bn + 2 * k1r + colc);
+      }
+      float4 hi[kItems], lo[kItems];
 #pragma unroll
       for (int it = 0; it < kItems; ++it) {
-        const int row = row0 + rloc[it];
-        ok[it] = row < m32;
-        rs[it] = 1.f;
-        if (p.k3 > 0 && ok[it]) {
+        float4 v = cur[it];
+        const int row = row0 + 32 * it;
+        const bool ok = col_ok && row < m32;
+        if (flags & kPanelBn) {
+          v.x = (v.x - mu.x) * sc.x + be.x; v.y = (v.y - mu.y) * sc.y + be.y;
+          v.z = (v.z - mu.z) * sc.z + be.z; v.w = (v.w - mu.w) * sc.w + be.w;
+        }
+        if (flags & kPanelRelu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if ((flags & kPanelRowScale) && ok) {
           const int deg = p.csc_ptr[row + 1] - p.csc_ptr[row];
-          rs[it] = p.rowscale_mode == 2 ? static_cast<float>(deg) : (deg > 0 ? 1.f : 0.f);
+          const float rs = p.rowscale_mode == 2 ? static_cast<float>(deg) : (deg > 0 ? 1.f : 0.f);
+          v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
         }
+        if (!ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        split_tf32(v.x, hi[it].x, lo[it].x); split_tf32(v.y, hi[it].y, lo[it].y);
+        split_tf32(v.z, hi[it].z, lo[it].z); split_tf32(v.w, hi[it].w, lo[it].w);
       }
-      for (int kc = 0; kc < chunks_per_tile; ++kc, ++g) {
-        const int k0 = kc * kKc;
-        const bool seg1 = k0 >= k1p && k0 < k1p + k2p;
-        const bool seg2 = k0 >= k1p + k2p;
-        const int col0 = k0 < k1p ? k0 : (seg1 ? k0 - k1p : k0 - k1p - k2p);
-        const int seg_len = seg1 ? p.k2 : p.k1;
-        asm volatile("cp.async.wait_group 1;" ::: "memory");  // this thread's items of chunk g have landed
-        const float* raw = s.raw + (g & 1u) * kABufFloats;
-        float4 hi[kItems], lo[kItems];
+      // wait until the MMAs of the previous use of this A stage have drained it
+      if (round >= 1u && !mbar_wait(&empty[stg], (round - 1u) & 1u)) timed_out = true;
+      float* dst_hi = s.a_base + stg * (2 * kABufFloats) + off0;
+      float* dst_lo = dst_hi + kABufFloats;
 #pragma unroll
-        for (int it = 0; it < kItems; ++it) {
-          float4 v = *reinterpret_cast<const float4*>(raw + off[it]);
-          const int c = col0 + kcol[it];
-          const bool valid = ok[it] && c < seg_len;
-          if (!seg1) {
-            if (has_bn) {
-              const float4 mu = *reinterpret_cast<const float4*>(s.bn + c);
-              const float4 sc = *reinterpret_cast<const float4*>(s.bn + p.k1 + c);
-              const float4 be = *reinterpret_cast<const float4*>(s.bn + 2 * p.k1 + c);
-              v.x = (v.x - mu.x) * sc.x + be.x; v.y = (v.y - mu.y) * sc.y + be.y;
-              v.z = (v.z - mu.z) * sc.z + be.z; v.w = (v.w - mu.w) * sc.w + be.w;
-            }
-            if (p.relu_a1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            if (seg2) { v.x *= rs[it]; v.y *= rs[it]; v.z *= rs[it]; v.w *= rs[it]; }
-          } else if (p.relu_a2) {
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-          }
-          if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
-          split_tf32(v.x, hi[it].x, lo[it].x); split_tf32(v.y, hi[it].y, lo[it].y);
-          split_tf32(v.z, hi[it].z, lo[it].z); split_tf32(v.w, hi[it].w, lo[it].w);
-        }
-        prefetch();  // the raw items are in registers: the slot can take chunk g + 2 right away
-        // wait until the MMAs of the previous use of this A stage have drained it
-        const uint32_t b = a_stages == 2 ? (g & 1u) : 0u;
-        const uint32_t use = a_stages == 2 ? (g >> 1) : g;
-        if (use >= 1u && !mbar_wait(&empty[b], (use - 1u) & 1u)) timed_out = true;
-        float* dst_hi = s.a_hi[b];
-        float* dst_lo = s.a_lo[b];
-#pragma unroll
-        for (int it = 0; it < kItems; ++it) {
-          *reinterpret_cast<float4*>(dst_hi + off[it]) = hi[it];
-          *reinterpret_cast<float4*>(dst_lo + off[it]) = lo[it];
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (MMA)
-        mbar_arrive(&full[b]);
+      for (int it = 0; it < kItems; ++it) {
+        *reinterpret_cast<float4*>(dst_hi + it * 1024) = hi[it];
+        *reinterpret_cast<float4*>(dst_lo + it * 1024) = lo[it];
       }
-      if (trace != nullptr && tid == 0 && tl < 32) trace[0 * 64 + tl * 2 + 1] = clock64();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (MMA)
+      mbar_arrive(&full[stg]);
+#pragma unroll
+      for (int it = 0; it < kItems; ++it) cur[it] = nxt[it];
+      if (++stg == a_stages) { stg = 0; ++round; }
+      if (++pi == chunks_per_tile) {
+        if (trace != nullptr && tid == 0 && tl < 32) trace[0 * 64 + tl * 2 + 1] = clock64();
+        pi = 0; ++tl;
+      }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
     // The whole warp runs this loop with uniform control flow and uniform operands (descriptors stay
     // in uniform registers, advancing one is a 32-bit add on its low word); only the tcgen05
-    // instructions themselves are predicated to lane 0.  Twelve MMAs per chunk, fully unrolled.
+    // instructions themselves are predicated to lane 0.  Three MMAs per k-step (hi*hi, lo*hi, hi*lo).
     const uint32_t leader = lane == 0 ? 1u : 0u;
     const uint32_t idesc = umma_idesc_tf32(kRows, np);
     const uint32_t w_panel16 = (static_cast<uint32_t>(np) * 128u) >> 4;  // one 32-float K block of W, in 16-byte units
     const uint64_t dw_hi0 = umma_desc(smem_u32(s.w_hi)), dw_lo0 = umma_desc(smem_u32(s.w_lo));
-    const uint64_t da_hi0[2] = {umma_desc(smem_u32(s.a_hi[0])), umma_desc(smem_u32(s.a_hi[1]))};
-    const uint64_t da_lo0[2] = {umma_desc(smem_u32(s.a_lo[0])), umma_desc(smem_u32(s.a_lo[1]))};
-    uint32_t g = 0;
+    const uint64_t da_hi_base = umma_desc(smem_u32(s.a_base));
+    constexpr uint32_t kStage16 = (2u * kABufFloats * 4u) >> 4, kImage16 = (kABufFloats * 4u) >> 4;  // 16-byte units
+    int stg = 0;
+    uint32_t round = 0;
     for (int64_t tl = 0; tl < my_tiles; ++tl) {
       const int ab = static_cast<int>(tl & 1);
       if (tl >= 2 && !mbar_wait(&acc_empty[ab], static_cast<uint32_t>(((tl >> 1) - 1) & 1))) timed_out = true;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_addr = tmem_d + static_cast<uint32_t>(ab * np);
       if (trace != nullptr && lane == 0 && tl < 32) trace[1 * 64 + tl * 2] = clock64();
-      for (int kc = 0; kc < chunks_per_tile; ++kc, ++g) {
-        const uint32_t b = a_stages == 2 ? (g & 1u) : 0u;
-        const uint32_t use = a_stages == 2 ? (g >> 1) : g;
-        if (!mbar_wait(&full[b], use & 1u)) timed_out = true;
+      for (int kc = 0; kc < chunks_per_tile; ++kc) {
+        const int ksteps = s.panel[kc].ksteps;
+        if (!mbar_wait(&full[stg], round & 1u)) timed_out = true;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t a_hi = b == 0 ? da_hi0[0] : da_hi0[1];
-        const uint64_t a_lo = b == 0 ? da_lo0[0] : da_lo0[1];
+        const uint64_t a_hi = da_hi_base + static_cast<uint64_t>(static_cast<uint32_t>(stg) * kStage16);
+        const uint64_t a_lo = a_hi + kImage16;
         const uint64_t w_hi = dw_hi0 + static_cast<uint64_t>(static_cast<uint32_t>(kc) * w_panel16);
         const uint64_t w_lo = dw_lo0 + static_cast<uint64_t>(static_cast<uint32_t>(kc) * w_panel16);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {  // a k-step is 32 bytes = 2 descriptor units further into the panel
-          umma_tf32_pred(d_addr, a_hi + 2 * jj, w_hi + 2 * jj, idesc, (kc > 0 || jj > 0) ? 1u : 0u, leader);
-          umma_tf32_pred(d_addr, a_lo + 2 * jj, w_hi + 2 * jj, idesc, 1u, leader);
-          umma_tf32_pred(d_addr, a_hi + 2 * jj, w_lo + 2 * jj, idesc, 1u, leader);
+          if (jj < ksteps) {
+            umma_tf32_pred(d_addr, a_hi + 2 * jj, w_hi + 2 * jj, idesc, (kc > 0 || jj > 0) ? 1u : 0u, leader);
+            umma_tf32_pred(d_addr, a_lo + 2 * jj, w_hi + 2 * jj, idesc, 1u, leader);
+            umma_tf32_pred(d_addr, a_hi + 2 * jj, w_lo + 2 * jj, idesc, 1u, leader);
+          }
         }
-        umma_commit_pred(&empty[b], leader);   // arrives when the MMAs above have finished reading the stage
+        umma_commit_pred(&empty[stg], leader);   // arrives when the MMAs above have finished reading the stage
+        if (++stg == a_stages) { stg = 0; ++round; }
       }
       umma_commit_pred(&acc_full[ab], leader);  // ... and when the whole tile's accumulator is complete
       if (trace != nullptr && lane == 0 && tl < 32) trace[1 * 64 + tl * 2 + 1] = clock64();
@@ -495,6 +509,7 @@ node_gemm_kernel(TcGemmParams p) {
         // of 32 rows x 16 bytes (8x fewer LSU wavefronts; the strided form bounded the kernel).
         float* st = s.stage + ew * (32 * 36);
         const int n_dbl = (n_blocks + 1) >> 1;
+        const int n_split = p.y2 != nullptr ? p.n_split : 0x7fffffff;
         const int64_t tile_row0 = tile * kRows + q * 32;
         for (int cd = half; cd < n_dbl; cd += 2) {
           uint32_t r0[16], r1[16];
@@ -533,7 +548,9 @@ node_gemm_kernel(TcGemmParams p) {
                 if (col + 2 >= p.n) v4.z = 0.f;
                 if (col + 3 >= p.n) v4.w = 0.f;
               }
-              *reinterpret_cast<float4*>(p.y + grow * p.ldy + col) = v4;
+              // split output: columns from n_split on go to the narrow tail array y2
+              if (col < n_split) *reinterpret_cast<float4*>(p.y + grow * p.ldy + col) = v4;
+              else *reinterpret_cast<float4*>(p.y2 + grow * p.ldy2 + (col - n_split)) = v4;
             }
           }
           __syncwarp();
@@ -641,14 +658,15 @@ node_gemm_kernel(TcGemmParams p) {
 
 size_t smem_bytes_for(int np, int kp, int a_stages, int staged = 0) {
   const size_t kp32 = (static_cast<size_t>(kp) + 31) & ~static_cast<size_t>(31);
-  return sizeof(float) * (2 * np * kp32 + (2 * a_stages + kRing) * kABufFloats + 16 * np + np + 3 * kp32 + 32 + 4 +
-                          (staged ? kStageFloats : 0)) + 64;
+  return sizeof(float) * (2 * np * kp32 + 2 * a_stages * kABufFloats + 16 * np + np + 3 * kp32 + 32 + 4 +
+                          (staged ? kStageFloats : 0)) + kMaxPanels * sizeof(PanelInfo) + 64;
 }
 
 int pick_a_stages(int np, int kp) {
   if (2 * np > 512) return 0;  // two TMEM accumulators
-  if (smem_bytes_for(np, kp, 2) <= 227 * 1024) return 2;
-  if (smem_bytes_for(np, kp, 1) <= 227 * 1024) return 1;
+  if (kp > kMaxPanels * kKc) return 0;
+  for (int st = kMaxStages; st >= 1; --st)
+    if (smem_bytes_for(np, kp, st) <= 227 * 1024) return st;
   return 0;
 }
 
@@ -662,13 +680,14 @@ bool tc_gemm_supported(const TcGemmShape& sh) {
   }
   if (!enabled) return false;
   if (sh.k1 < 4 || sh.k1 % 4 != 0 || sh.k2 % 4 != 0 || sh.n < 1) return false;
-  const int np = tc_padded_n(sh.n), kp = tc_padded_k(sh.k1, sh.k2, sh.k3);
+  if (sh.kt % 4 != 0) return false;
+  const int np = tc_padded_n(sh.n), kp = tc_padded_k(sh);
   if (np > 256) return false;
   return pick_a_stages(np, kp) > 0;
 }
 
 size_t tc_pack_floats(const TcGemmShape& sh) {
-  return 2 * static_cast<size_t>(tc_padded_n(sh.n)) * tc_padded_k(sh.k1, sh.k2, sh.k3);
+  return 2 * static_cast<size_t>(tc_padded_n(sh.n)) * tc_padded_k(sh);
 }
 
 int tc_fold_weights(const float* w_m, int64_t ld_m, const float* w_t, int64_t ld_t, int c_out, int p, int c,
@@ -680,7 +699,7 @@ int tc_fold_weights(const float* w_m, int64_t ld_m, const float* w_t, int64_t ld
 }
 
 int tc_pack_weights(const TcWeightBlocks& blocks, const TcGemmShape& sh, float* wpack, cudaStream_t stream) {
-  const int np = tc_padded_n(sh.n), kp = tc_padded_k(sh.k1, sh.k2, sh.k3);
+  const int np = tc_padded_n(sh.n), kp = tc_padded_k(sh);
   RGNN_PROFILE("weight_prep", stream);
   pack_weights_kernel<<<div_up(np * kp, 256), 256, 0, stream>>>(blocks, np, kp, wpack);
   RGNN_LAUNCH_CHECK();
@@ -699,14 +718,19 @@ int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
   if (p.m <= 0) return RGNN_OK;
   if (g_trace_buffer != nullptr && strcmp(tag, g_trace_tag) == 0) { p.trace = g_trace_buffer; g_trace_buffer = nullptr; }
   p.np = tc_padded_n(p.n);
-  p.kp = tc_padded_k(p.k1, p.k2, p.k3);
+  p.kp = tc_seg_pad(p.k1) + tc_seg_pad(p.k2) + tc_seg_pad(p.kt) + tc_seg_pad(p.k3);
   if (p.n_store < p.n) p.n_store = p.n;
   p.a_stages = pick_a_stages(p.np, p.kp);
   if (p.a_stages == 0) return RGNN_ERR_UNSUPPORTED;
   // coalesced (staged) epilogue when there is neither residual nor BatchNorm sums, the rows allow
   // 16-byte stores and the transpose buffers still fit
-  p.staged_epilogue = (p.residual == nullptr && p.bn_partial == nullptr && (p.ldy & 3) == 0 && (p.n_store & 3) == 0 &&
-                       smem_bytes_for(p.np, p.kp, p.a_stages, 1) <= 227 * 1024) ? 1 : 0;
+  p.staged_epilogue = (p.residual == nullptr && p.bn_partial == nullptr && (p.ldy & 3) == 0 && (p.n_store & 3) == 0) ? 1 : 0;
+  if (p.staged_epilogue) {
+    // the transpose buffers may cost one A stage
+    while (p.a_stages > 1 && smem_bytes_for(p.np, p.kp, p.a_stages, 1) > 227 * 1024) --p.a_stages;
+    if (smem_bytes_for(p.np, p.kp, p.a_stages, 1) > 227 * 1024) p.staged_epilogue = 0;
+  }
+  if (p.y2 != nullptr && (!p.staged_epilogue || (p.n_split & 3) != 0 || (p.ldy2 & 3) != 0)) return RGNN_ERR_UNSUPPORTED;
   const size_t smem = smem_bytes_for(p.np, p.kp, p.a_stages, p.staged_epilogue);
   static size_t configured = 0;
   if (smem > configured) {

@@ -7,15 +7,16 @@
 
 namespace rgnn {
 
-// logical shape of one contraction: K = k1 + k2 + k3 (k3 = 0 or k1: rowscale * a1), N outputs
+// logical shape of one contraction: K = k1 + k2 + kt + k3 (kt: narrow tail columns of the second
+// operand kept in their own array; k3 = 0 or k1: rowscale * a1), N outputs
 struct TcGemmShape {
-  int32_t k1 = 0, k2 = 0, k3 = 0, n = 0;
+  int32_t k1 = 0, k2 = 0, kt = 0, k3 = 0, n = 0;
 };
 
 inline int tc_padded_n(int n) { return (n + 15) & ~15; }
 // every K segment is padded to whole 32-float chunks (one 128-byte swizzled panel column)
 inline int tc_seg_pad(int k) { return (k + 31) & ~31; }
-inline int tc_padded_k(int k1, int k2, int k3) { return tc_seg_pad(k1) + tc_seg_pad(k2) + tc_seg_pad(k3); }
+inline int tc_padded_k(const TcGemmShape& s) { return tc_seg_pad(s.k1) + tc_seg_pad(s.k2) + tc_seg_pad(s.kt) + tc_seg_pad(s.k3); }
 
 // one block of source weights copied into the packed image: rows x cols of a row-major matrix
 // (row stride ld) placed at K offset k_offset
@@ -26,7 +27,7 @@ struct TcWeightBlock {
   int32_t accumulate;  // add onto what earlier blocks put at these positions instead of replacing it
 };
 struct TcWeightBlocks {
-  TcWeightBlock block[3];
+  TcWeightBlock block[4];
   int32_t count;
 };
 
@@ -34,7 +35,8 @@ struct TcGemmParams {
   const float* a1 = nullptr; int64_t lda1 = 0; int32_t k1 = 0;   // 16-byte aligned rows, k1 % 4 == 0
   const int32_t* a1_rows = nullptr;                              // optional gather map for a1 / residual rows
   const float* a2 = nullptr; int64_t lda2 = 0; int32_t k2 = 0;   // optional, k2 % 4 == 0
-  int32_t k3 = 0;                                                // 0, or k1: third segment rowscale * a1
+  const float* at = nullptr; int64_t ldat = 0; int32_t kt = 0;   // optional narrow tail of a2 (kt % 4 == 0, kt <= ldat)
+  int32_t k3 = 0;                                                // 0, or k1: last segment rowscale * a1
   const int32_t* csc_ptr = nullptr; int32_t rowscale_mode = 0;   // 1: in-degree > 0, 2: in-degree
   const float* a1_mean = nullptr; const float* a1_scale = nullptr; const float* a1_beta = nullptr;
   int32_t relu_a1 = 0, relu_a2 = 0;
@@ -45,6 +47,7 @@ struct TcGemmParams {
   const float* res_mean = nullptr; const float* res_scale = nullptr; const float* res_beta = nullptr;
   int32_t res_relu = 0;
   float* y = nullptr; int64_t ldy = 0; int32_t n_store = 0;      // columns written (>= n; extras are zeros)
+  float* y2 = nullptr; int64_t ldy2 = 0; int32_t n_split = 0;    // optional: columns >= n_split go to y2[:, col - n_split]
   double* bn_partial = nullptr;                                  // [tc_tiles(m)][2][n] column sums / squares
   int64_t m = 0;
   int32_t* status = nullptr;                                     // device flag set if a barrier wait timed out

@@ -78,8 +78,8 @@ def test_workspace_sizes_are_monotone_and_aligned(lib):
     d.conv_type, d.aggr, d.in_channels, d.out_channels, d.edge_dim = 0, 0, 64, 64, 2
     d.pre_layers = d.post_layers = 1
     w1 = lib.rgnn_conv_workspace_bytes(C.byref(d), 100_000, 1_600_000)
-    # A, B, M [N, 132] fp32 + edge attributes in slot order
-    assert w1 >= 3 * 100_000 * 132 * 4 + 1_600_000 * 2 * 4
+    # B, M in the split layout ([N, 128] main + [N, 4] tail, fp32) + edge attributes in slot order
+    assert w1 >= 2 * 100_000 * 132 * 4 + 1_600_000 * 2 * 4
     # tensor-core weight images of the factored path: W_s [144 x 64] and update [64 x 224], hi + lo
     assert lib.rgnn_conv_packed_bytes(C.byref(d)) >= 2 * 4 * (144 * 64 + 64 * 224)
     d.pre_layers = 2   # general path: two [E, 132] per-edge activation buffers, no tensor-core images

@@ -239,6 +239,8 @@ def test_conv_known_answers(ops):
     ("MPNNConv", "max", 1, 1, 64, 64, 2), ("MPNNConv", "add", 1, 2, 16, 24, 4), ("MPNNConv", "mean", 2, 1, 8, 8, 2),
     ("MPNNConv", "min", 3, 2, 5, 7, 3), ("RadarPointGNNConv", "max", 1, 1, 32, 32, 2),
     ("RadarPointGNNConv", "add", 2, 2, 12, 12, 4), ("MPNNConv", "max", 1, 1, 128, 128, 2),
+    # split message layout (C = 64 MPNNConv on the tensor-core path): every aggregation and tail width
+    ("MPNNConv", "add", 1, 1, 64, 64, 4), ("MPNNConv", "mean", 1, 2, 64, 48, 3), ("MPNNConv", "min", 1, 1, 64, 32, 1),
 ])
 def test_conv_random_vs_oracle(ops, kind, aggr, pre, post, c, cout, de):
     g = torch.Generator().manual_seed(c * 7 + de)
@@ -261,6 +263,27 @@ def test_conv_random_vs_oracle(ops, kind, aggr, pre, post, c, cout, de):
     else:
         want = mo.radar_point_gnn_conv_forward(params, x, ei, ea, aggr, dtype=torch.float64)
     cp = _conv_params(ops, params, {"kind": kind, "aggr": aggr})
+    got = ops.conv_forward(cp, x.to(DEV), ops.csc_build(ei.to(DEV), n), ea.to(DEV)).cpu()
+    assert mo.relative_error(got, want) <= 2e-5
+    assert torch.isfinite(got).all()
+
+
+@pytest.mark.parametrize("aggr", ["max", "add", "mean"])
+def test_conv_split_layout_high_in_degree(ops, aggr):
+    """Warp-per-node aggregate: in-degrees far above 32 (several slot batches per node), a node with exactly
+    32 and 33 incoming edges, and nodes without any."""
+    g = torch.Generator().manual_seed(5)
+    n, c, de = 150, 64, 2
+    dst = torch.cat([torch.randint(0, 100, (12000,), generator=g), torch.full((32,), 100), torch.full((33,), 101)])
+    src = torch.randint(0, n, (dst.numel(),), generator=g)
+    ei = torch.stack([src, dst])
+    x = torch.randn(n, c, generator=g)
+    ea = torch.randn(ei.shape[1], de, generator=g)
+    p = 2 * c + de
+    params = {"pre_mlp.0.weight": torch.randn(p, p, generator=g) / p ** 0.5, "pre_mlp.0.bias": torch.randn(p, generator=g) * 0.1,
+              "post_mlp.0.weight": torch.randn(c, p + c, generator=g) / (p + c) ** 0.5, "post_mlp.0.bias": torch.randn(c, generator=g) * 0.1}
+    want = mo.mpnn_conv_forward(params, x, ei, ea, aggr, dtype=torch.float64)
+    cp = _conv_params(ops, params, {"kind": "MPNNConv", "aggr": aggr})
     got = ops.conv_forward(cp, x.to(DEV), ops.csc_build(ei.to(DEV), n), ea.to(DEV)).cpu()
     assert mo.relative_error(got, want) <= 2e-5
     assert torch.isfinite(got).all()
