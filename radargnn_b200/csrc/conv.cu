@@ -270,61 +270,94 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
   constexpr float kInit = MODE == RGNN_AGGR_MAX ? -INFINITY : (MODE == RGNN_AGGR_MIN ? INFINITY : 0.f);
   const float4 init4 = make_float4(kInit, kInit, kInit, kInit);
   const float* bcol = bm + 4 * q;
+  constexpr int kPasses = kSplitRows / 16;
+  const int row_base = blockIdx.x * kSplitRows + warp * 4 + quarter;
 
-  for (int it = 0; it < kSplitRows / 16; ++it) {
-    const int row = blockIdx.x * kSplitRows + it * 16 + warp * 4 + quarter;
+  // Software pipeline over the passes: the row pointers run two passes ahead and the first 16 slots
+  // (lane q holds slots q and q + 8: source index, edge attributes) one pass ahead, so that a pass starts
+  // its gathers without waiting for an index load.
+  struct SlotRegs { int src[2]; float e[2][DE]; };
+  auto load_ptr = [&](int pass, int& beg, int& deg) {
+    const int row = row_base + pass * 16;
+    beg = 0; deg = 0;
+    if (pass < kPasses && row < n_nodes) { beg = csc_ptr[row]; deg = csc_ptr[row + 1] - beg; }
+  };
+  auto load_slots = [&](int beg, int deg, int b, SlotRegs& r) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      r.src[h] = 0;
+#pragma unroll
+      for (int d = 0; d < DE; ++d) r.e[h][d] = 0.f;
+      if (b + 8 * h + q < deg) {
+        const int slot = beg + b + 8 * h + q;
+        r.src[h] = csc_src[slot];
+        const float* e = ea + static_cast<int64_t>(slot) * DE;
+#pragma unroll
+        for (int d = 0; d < DE; ++d) r.e[h][d] = e[d];
+      }
+    }
+  };
+  int beg, deg, beg1, deg1, beg2, deg2;
+  load_ptr(0, beg, deg);
+  load_ptr(1, beg1, deg1);
+  SlotRegs pre;
+  load_slots(beg, deg, 0, pre);
+
+  for (int it = 0; it < kPasses; ++it) {
+    const int row = row_base + it * 16;
     const bool live = row < n_nodes;
-    int beg = 0, deg = 0;
-    if (live) { beg = csc_ptr[row]; deg = csc_ptr[row + 1] - beg; }
+    load_ptr(it + 2, beg2, deg2);
+    SlotRegs cur = pre;
+    load_slots(beg1, deg1, 0, pre);   // next pass (zeros past the last pass)
     const int nmax = __reduce_max_sync(0xffffffffu, deg);
     float4 acc[4] = {init4, init4, init4, init4};
     float4 tacc = init4;
-    for (int b = 0; b < nmax; b += 8) {
-      // lane q of the quarter holds slot b + q of its row
-      int my_src = 0;
-      float my_e[DE];
+    for (int b = 0; b < nmax; b += 16) {
+      if (b > 0) load_slots(beg, deg, b, cur);   // in-degree above 16: not prefetched
+      // tail channels, slot-parallel
 #pragma unroll
-      for (int d = 0; d < DE; ++d) my_e[d] = 0.f;
-      if (b + q < deg) {
-        const int slot = beg + b + q;
-        my_src = csc_src[slot];
-        const float* e = ea + static_cast<int64_t>(slot) * DE;
+      for (int h = 0; h < 2; ++h) {
+        if (b + 8 * h + q < deg) {
+          float4 t = ld4(bt + static_cast<int64_t>(cur.src[h]) * 4);
 #pragma unroll
-        for (int d = 0; d < DE; ++d) my_e[d] = e[d];
-        float4 t = ld4(bt + static_cast<int64_t>(my_src) * 4);
-#pragma unroll
-        for (int d = 0; d < DE; ++d) t = fma4(my_e[d], wt[d], t);
-        tacc = combine4<MODE>(tacc, t);
+          for (int d = 0; d < DE; ++d) t = fma4(cur.e[h][d], wt[d], t);
+          tacc = combine4<MODE>(tacc, t);
+        }
       }
+      for (int g = 0; g < 4; ++g) {
+        if (b + 4 * g >= nmax) break;   // warp-uniform
+        const int sreg = g < 2 ? cur.src[0] : cur.src[1];
+        float ereg[DE];
 #pragma unroll
-      for (int j0 = 0; j0 < 8; j0 += 4) {
-        if (b + j0 < nmax) {   // warp-uniform
-          float4 v[4][4];
+        for (int d = 0; d < DE; ++d) ereg[d] = g < 2 ? cur.e[0][d] : cur.e[1][d];
+        const int l0 = (4 * g) & 7;
+        float4 v[4][4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int sidx = __shfl_sync(0xffffffffu, my_src, j0 + u, 8);
-            const bool on = b + j0 + u < deg;
-            const float* rp = bcol + static_cast<int64_t>(sidx) * kSplitMain;
+        for (int u = 0; u < 4; ++u) {
+          const int sidx = __shfl_sync(0xffffffffu, sreg, l0 + u, 8);
+          const bool on = b + 4 * g + u < deg;
+          const float* rp = bcol + static_cast<int64_t>(sidx) * kSplitMain;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[u][i] = on ? ld4(rp + 32 * i) : init4;
+          for (int i = 0; i < 4; ++i) v[u][i] = on ? ld4(rp + 32 * i) : init4;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int d = 0; d < DE; ++d) {
+            const float ed = __shfl_sync(0xffffffffu, ereg[d], l0 + u, 8);   // 0 for slots beyond the row's degree
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[u][i] = fma4x2(ed, w[d][i], v[u][i]);
           }
+        }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-#pragma unroll
-            for (int d = 0; d < DE; ++d) {
-              const float ed = __shfl_sync(0xffffffffu, my_e[d], j0 + u, 8);   // 0 for slots beyond the row's degree
-#pragma unroll
-              for (int i = 0; i < 4; ++i) v[u][i] = fma4x2(ed, w[d][i], v[u][i]);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            acc[i] = combine4x2<MODE>(acc[i], v[0][i], v[1][i]);
-            acc[i] = combine4x2<MODE>(acc[i], v[2][i], v[3][i]);
-          }
+        for (int i = 0; i < 4; ++i) {
+          acc[i] = combine4x2<MODE>(acc[i], v[0][i], v[1][i]);
+          acc[i] = combine4x2<MODE>(acc[i], v[2][i], v[3][i]);
         }
       }
     }
+    const int deg_row = deg;
+    beg = beg1; deg = deg1; beg1 = beg2; deg1 = deg2;
     // tail: fixed-order butterfly over the quarter's 8 lanes (= slots)
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
@@ -343,18 +376,18 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
     float4 r[4], rt = make_float4(0.f, 0.f, 0.f, 0.f);  // torch_scatter: empty segments aggregate to 0
 #pragma unroll
     for (int i = 0; i < 4; ++i) r[i] = rt;
-    if (deg > 0) {
+    if (deg_row > 0) {
       if (MODE == RGNN_AGGR_MAX || MODE == RGNN_AGGR_MIN) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) r[i] = add4(bmain[i], acc[i]);
         rt = add4(btail, tacc);
       } else if (MODE == RGNN_AGGR_ADD) {
-        const float fd = static_cast<float>(deg);
+        const float fd = static_cast<float>(deg_row);
 #pragma unroll
         for (int i = 0; i < 4; ++i) r[i] = fma4(fd, bmain[i], acc[i]);
         rt = fma4(fd, btail, tacc);
       } else {
-        const float inv = 1.f / static_cast<float>(deg);
+        const float inv = 1.f / static_cast<float>(deg_row);
 #pragma unroll
         for (int i = 0; i < 4; ++i) r[i] = fma4(inv, acc[i], bmain[i]);
         rt = fma4(inv, tacc, btail);

@@ -59,29 +59,6 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// warp-uniform variants: every lane executes the surrounding code, `leader` selects the issuing lane
-__device__ __forceinline__ void umma_tf32_pred(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                               uint32_t accumulate, uint32_t leader) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
-      : "memory");
-}
-
 __device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t leader) {
   asm volatile(
       "{\n\t"
@@ -90,10 +67,6 @@ __device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t leader)
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
       "}\n" ::"r"(smem_u32(bar)), "r"(leader)
       : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -170,28 +143,38 @@ fold_weights_kernel(const float* __restrict__ w_m, int64_t ld_m, const float* __
 
 // ---- the GEMM ------------------------------------------------------------------------------
 // K is laid out segment by segment, [a1 | a2 | a_tail | rowscale * a1], each padded to whole panels of
-// 32 floats (one 128-byte swizzled column block), so a panel lies in exactly one segment.
+// 32 floats, so a panel (128 rows x 32 floats) lies in exactly one segment.
 //
-// Warp roles (544 threads, one CTA per SM, persistent over 128-row tiles):
-//   warps 0-7   producers: one panel (128 rows x 32 floats) per barrier round.  Each thread loads its four
-//               16-byte items of the NEXT panel straight into registers (coalesced LDG.128, 8 threads per
-//               128-byte row segment) before it transforms (BatchNorm + ReLU on load, row scale), splits
-//               and stores the current one into the swizzled hi / lo stage -- the global latency of panel
-//               g + 1 hides behind the round of panel g; no staging ring, ~60 instructions per round.
-//   warps 8-15  epilogue:  TMEM -> registers -> global (+ BatchNorm column sums); two warps per TMEM lane
+// The A operand lives in TENSOR MEMORY (tcgen05.mma with A from TMEM, W from shared memory):
+//   global --cp.async--> raw fp32 panel ring in shared memory (up to 6 x 16 KB in flight per SM: enough
+//   to cover DRAM latency at full bandwidth) --converter warps: BatchNorm + ReLU on load, row scale,
+//   hi / lo split--> tcgen05.st into a TMEM A stage (64 columns: 32 hi + 32 lo) --> MMA.
+// Shared memory then only holds W (resident) and the raw ring; there is no swizzled A stage, no
+// generic->async proxy fence, and TMEM (512 columns) has room for the two accumulators plus 3-4 A stages.
+//
+// Warp roles (672 threads, one CTA per SM, persistent over 128-row tiles):
+//   warps 0-3   loaders: cp.async 16-byte items of a panel into the ring slot (8 lanes per 128-byte row
+//               segment, zero fill for rows / columns beyond the operand), completion via
+//               cp.async.mbarrier.arrive on raw_full[slot]
+//   warps 4-11  converters, two groups of four (one warp per TMEM lane quarter) alternating panels:
+//               thread = row, 32 floats from the ring (swizzled: conflict-free), transform, split,
+//               2 x 2 tcgen05.st.x16 -> a_full[stage]; the slot goes back to the loaders (raw_empty)
+//   warps 12-19 epilogue: TMEM -> registers -> global (+ BatchNorm column sums); two warps per TMEM lane
 //               quarter, alternating 16-column blocks
-//   warp  16    MMA issuer (one lane): tcgen05.mma per 8-float k-step, tcgen05.commit to the barriers
-// Hand-offs are mbarriers only: full[s] (producers -> MMA), empty[s] (MMA done -> producers),
-// acc_full[a] (MMA -> epilogue), acc_empty[a] (epilogue -> MMA).  Up to three A stages and two TMEM
-// accumulators, so loads, conversion, MMAs and the epilogue of consecutive tiles overlap.
-constexpr int kMaxStages = 3;
-constexpr int kProducerWarps = 8;
-constexpr int kProducerThreads = kProducerWarps * 32;
+//   warp  20    MMA issuer (one lane): per k-step hi*hi + lo*hi + hi*lo, tcgen05.commit -> a_empty / acc_full
+constexpr int kMaxRaw = 6;
+constexpr int kMaxAStages = 4;
+constexpr int kLoaderWarps = 4, kConvWarps = 8;
+constexpr int kLoaderThreads = kLoaderWarps * 32;
+constexpr int kConvGroupThreads = 128;            // one converter group = 4 warps
 constexpr int kEpilogueThreads = 256;
-constexpr int kItems = 1024 / kProducerThreads;   // float4 items of a panel per producer thread
-constexpr int kGemmThreads = kProducerThreads + kEpilogueThreads + 32;
-constexpr int kMmaWarp = (kProducerThreads + kEpilogueThreads) / 32;
+constexpr int kEpiWarp0 = kLoaderWarps + kConvWarps;
+constexpr int kProducerWarps = kEpiWarp0;         // warps in front of the epilogue warps
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kMmaWarp = kEpiWarp0 + kEpilogueThreads / 32;
+constexpr int kGemmThreads = (kMmaWarp + 1) * 32;
 constexpr int kMaxPanels = 16;
+constexpr int kAStageCols = 64;                   // TMEM columns of one A stage: 32 hi + 32 lo
 
 enum PanelFlags : int32_t { kPanelBn = 1, kPanelRelu = 2, kPanelRowScale = 4, kPanelGather = 8 };
 
@@ -206,25 +189,26 @@ struct PanelInfo {
 
 struct SmemLayout {
   float* w_hi; float* w_lo;
-  float* a_base;                   // converted panels: stage i = hi image at a_base + i * 2 * kABufFloats, lo image after it
+  float* raw;                      // [raw_slots][128 x 32] fp32 panels as loaded (row r chunk c at c ^ (r % 8))
   float* col_sum;                  // [2 accumulators][4 quarters][np]
   float* col_sq;
   float* bias;                     // [np]
   float* bn;                       // [3][k1] mean | scale | beta of the a1 transform
   float* stage;                    // optional: 8 epilogue warps x [32][36] transpose buffers (coalesced stores)
   PanelInfo* panel;                // [kMaxPanels]
-  uint64_t* bar;                   // full[3], empty[3], acc_full[2], acc_empty[2]
+  uint64_t* bar;                   // raw_full[6], raw_empty[6], a_full[4], a_empty[4], acc_full[2], acc_empty[2]
   uint32_t* tmem_base;
 };
 
 constexpr int kStageFloats = 8 * 32 * 36;
+constexpr int kBarCount = 2 * kMaxRaw + 2 * kMaxAStages + 4;
 
-__device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int np, int kp32, int a_stages, int k1, int staged) {
+__device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int np, int kp32, int raw_slots, int k1, int staged) {
   SmemLayout s;
   float* f = reinterpret_cast<float*>(base);
   s.w_hi = f; f += static_cast<size_t>(np) * kp32;
   s.w_lo = f; f += static_cast<size_t>(np) * kp32;
-  s.a_base = f; f += static_cast<size_t>(a_stages) * 2 * kABufFloats;
+  s.raw = f; f += static_cast<size_t>(raw_slots) * kABufFloats;
   s.col_sum = f; f += 8 * np;
   s.col_sq = f; f += 8 * np;
   s.bias = f; f += np;
@@ -232,7 +216,7 @@ __device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int np, in
   s.stage = nullptr;
   if (staged) { s.stage = f; f += kStageFloats; }
   s.panel = reinterpret_cast<PanelInfo*>(f); f += kMaxPanels * (sizeof(PanelInfo) / sizeof(float));
-  s.bar = reinterpret_cast<uint64_t*>(f); f += 24;
+  s.bar = reinterpret_cast<uint64_t*>(f); f += 2 * kBarCount;
   s.tmem_base = reinterpret_cast<uint32_t*>(f);
   return s;
 }
@@ -241,34 +225,57 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 
+// arrive on `bar` once every cp.async this thread has issued so far has landed (counts as one of the
+// barrier's expected arrivals)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ float4 ldg_f4(const float* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
+// 16 consecutive TMEM columns of this thread's lane (lane = 32 * (warp % 4) + lane id)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
+        "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+
+// D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void umma_tf32_ts_pred(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 node_gemm_kernel(TcGemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int np = p.np, kp = p.kp, kp32 = (p.kp + 31) & ~31;
-  const int a_stages = p.a_stages;
-  const SmemLayout s = carve_smem(smem_raw, np, kp32, a_stages, p.k1, p.staged_epilogue);
+  const int a_stages = p.a_stages, raw_slots = p.raw_slots;
+  const SmemLayout s = carve_smem(smem_raw, np, kp32, raw_slots, p.k1, p.staged_epilogue);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int acc_cols = 2 * np;
-  const int tmem_cols = acc_cols <= 32 ? 32 : (acc_cols <= 64 ? 64 : (acc_cols <= 128 ? 128 : (acc_cols <= 256 ? 256 : 512)));
-  uint64_t* full = s.bar;            // [3]
-  uint64_t* empty = s.bar + 3;       // [3]
-  uint64_t* acc_full = s.bar + 6;    // [2]
-  uint64_t* acc_empty = s.bar + 8;   // [2]
+  constexpr int tmem_cols = 512;
+  uint64_t* raw_full = s.bar;                          // [kMaxRaw]
+  uint64_t* raw_empty = s.bar + kMaxRaw;               // [kMaxRaw]
+  uint64_t* a_full = s.bar + 2 * kMaxRaw;              // [kMaxAStages]
+  uint64_t* a_empty = a_full + kMaxAStages;            // [kMaxAStages]
+  uint64_t* acc_full = a_empty + kMaxAStages;          // [2]
+  uint64_t* acc_empty = acc_full + 2;                  // [2]
 
   // ---- one-time setup: barriers, TMEM, resident weights, bias, BatchNorm-on-load parameters ------
   if (tid == 0) {
-    for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], kProducerThreads); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kMaxRaw; ++i) { mbar_init(&raw_full[i], kLoaderThreads); mbar_init(&raw_empty[i], kConvGroupThreads); }
+    for (int i = 0; i < kMaxAStages; ++i) { mbar_init(&a_full[i], kConvGroupThreads); mbar_init(&a_empty[i], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_init(&acc_empty[0], kEpilogueThreads); mbar_init(&acc_empty[1], kEpilogueThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -278,7 +285,7 @@ node_gemm_kernel(TcGemmParams p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   const int k1p = (p.k1 + 31) & ~31, k2p = (p.k2 + 31) & ~31, ktp = (p.kt + 31) & ~31;
-  const int chunks_per_tile = (kp + kKc - 1) / kKc;
+  const int panels = (kp + kKc - 1) / kKc;
   {
     // resident weights: fire-and-forget cp.async (no register staging), waited for before the barrier
     const int total16 = (2 * np * kp32) >> 2;
@@ -292,7 +299,7 @@ node_gemm_kernel(TcGemmParams p) {
         s.bn[i] = p.a1_mean[i]; s.bn[k1r + i] = p.a1_scale[i]; s.bn[2 * k1r + i] = p.a1_beta[i];
       }
     }
-    if (tid < chunks_per_tile && tid < kMaxPanels) {
+    if (tid < panels && tid < kMaxPanels) {
       // which segment panel `tid` lies in
       const int k0 = tid * kKc;
       PanelInfo pi;
@@ -315,142 +322,147 @@ node_gemm_kernel(TcGemmParams p) {
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // W: generic-proxy writes -> async proxy (MMA)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *s.tmem_base;
+  const uint32_t a_col0 = static_cast<uint32_t>(2 * np);   // A stages follow the two accumulators
 
   const int64_t n_tiles = (p.m + kRows - 1) / kRows;
   const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int total = static_cast<int>(my_tiles) * panels;   // panels this CTA streams
+  const int m32 = static_cast<int>(p.m);
   bool timed_out = false;
   // optional timeline of CTA 0 (debug): trace[role * 64 + tile * 2 + {0, 1}] = clock64
   long long* trace = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
   if (trace != nullptr && tid == 0) trace[3 * 64] = clock64();
 
-  if (warp < kProducerWarps) {
-    // =========================== producers ===========================
-    // thread -> (16-byte chunk c of the 128-byte row segment, rows r0 + 32 i): eight consecutive threads
-    // read one contiguous 128-byte row segment and write one swizzled 128-byte stage row
-    const int c = tid & 7, r0 = tid >> 3;
-    const int off0 = (r0 >> 3) * 256 + (r0 & 7) * 32 + ((c ^ (r0 & 7)) << 2);
-    const int m32 = static_cast<int>(p.m);
-    const int k1r = (p.k1 + 3) & ~3;
-    const int64_t total = my_tiles * chunks_per_tile;
-
-    auto load_panel = [&](int64_t tl, int pi, float4 (&v)[kItems]) {
+  if (warp < kLoaderWarps) {
+    // =========================== loaders ===========================
+    // warp w streams rows 32 w .. 32 w + 31 of every panel: item i of a lane = row 32 w + 4 i + lane / 8,
+    // 16-byte chunk lane % 8 (a warp instruction covers four whole 128-byte row segments)
+    const int c = lane & 7;
+    const int rsub = warp * 32 + (lane >> 3);
+    const uint32_t raw_addr = smem_u32(s.raw);
+    int tl = 0, pi = 0, slot = 0;
+    uint32_t wrap = 0;   // how often the ring has wrapped
+    int64_t rr[8];       // source rows of this thread's items (through the optional gather map), per tile
+    bool rok[8];
+    auto tile_rows = [&](int t) {
+      const int row0 = static_cast<int>(blockIdx.x + static_cast<int64_t>(t) * gridDim.x) * kRows;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = row0 + rsub + 4 * i;
+        rok[i] = row < m32;
+        const int rc = rok[i] ? row : 0;
+        rr[i] = p.a1_rows != nullptr ? static_cast<int64_t>(p.a1_rows[rc]) : static_cast<int64_t>(rc);
+      }
+    };
+    if (total > 0) tile_rows(0);
+    for (int g = 0; g < total; ++g) {
+      if (trace != nullptr && tid == 0 && pi == 0 && tl < 32) trace[0 * 64 + tl * 2] = clock64();
+      if (wrap >= 1u && !mbar_wait(&raw_empty[slot], (wrap - 1u) & 1u)) timed_out = true;
       const PanelInfo& info = s.panel[pi];
-      const int row0 = static_cast<int>(blockIdx.x + tl * gridDim.x) * kRows + r0;
+      const int row0 = static_cast<int>(blockIdx.x + static_cast<int64_t>(tl) * gridDim.x) * kRows;
       const bool col_ok = 4 * c < info.valid;
       const float* colp = info.base + info.col0 + 4 * c;
       const bool gather = (info.flags & kPanelGather) != 0;
+      const int64_t ld = info.ld;
+      const uint32_t slot_addr = raw_addr + static_cast<uint32_t>(slot) * (kABufFloats * 4u);
 #pragma unroll
-      for (int it = 0; it < kItems; ++it) {
-        const int row = row0 + 32 * it;
-        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col_ok && row < m32) {
-          const int64_t rr = gather ? static_cast<int64_t>(p.a1_rows[row]) : static_cast<int64_t>(row);
-          v[it] = ldg_f4(colp + rr * info.ld);
-        }
+      for (int i = 0; i < 8; ++i) {
+        const int rl = rsub + 4 * i;
+        const bool ok = col_ok && rok[i];
+        const int64_t r = gather ? rr[i] : static_cast<int64_t>(row0 + rl);
+        const float* src = ok ? colp + r * ld : p.a1;
+        cp_async16(slot_addr + static_cast<uint32_t>(rl * 32 + ((c ^ (rl & 7)) << 2)) * 4u, src, ok ? 16u : 0u);
       }
-    };
-    // L2 prefetch of a whole tile's A rows, two tiles ahead of the register stream
-    const int lines1 = (p.k1 * 4 + 127) >> 7, lines2 = (p.k2 * 4 + 127) >> 7;
-    auto l2_prefetch_tile = [&](int64_t tl) {
-      if (tl >= my_tiles) return;
-      const int row = static_cast<int>(blockIdx.x + tl * gridDim.x) * kRows + (tid & 127);
-      if (row >= m32) return;
-      const int64_t arow = p.a1_rows != nullptr ? p.a1_rows[row] : row;
-      const float* r1 = p.a1 + arow * p.lda1;
-      const float* r2 = p.a2 != nullptr ? p.a2 + static_cast<int64_t>(row) * p.lda2 : nullptr;
-      for (int l = tid >> 7; l < lines1 + lines2; l += 2) {
-        const float* addr = l < lines1 ? r1 + l * 32 : r2 + (l - lines1) * 32;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
-      }
-      if (p.at != nullptr && (tid >> 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.at + static_cast<int64_t>(row) * p.ldat));
-    };
-    l2_prefetch_tile(1);
-
-    float4 cur[kItems], nxt[kItems];
-    int64_t ld_tl = 0; int ld_pi = 0;      // next panel to load
-    if (total > 0) {
-      load_panel(0, 0, cur);
-      if (++ld_pi == chunks_per_tile) { ld_pi = 0; ++ld_tl; }
-    }
-    int stg = 0;            // stage of panel g
-    uint32_t round = 0;     // how often the stage ring has wrapped
-    int64_t tl = 0; int pi = 0;
-    for (int64_t g = 0; g < total; ++g) {
-      if (pi == 0) {
-        if (trace != nullptr && tid == 0 && tl < 32) trace[0 * 64 + tl * 2] = clock64();
-        l2_prefetch_tile(tl + 2);
-      }
-      if (ld_tl < my_tiles) {
-        load_panel(ld_tl, ld_pi, nxt);
-        if (++ld_pi == chunks_per_tile) { ld_pi = 0; ++ld_tl; }
-      }
-      // ---- transform + split the current panel ------------------------------------------------
-      const PanelInfo& info = s.panel[pi];
-      const int flags = info.flags;
-      const int colc = info.col0 + 4 * c;
-      const bool col_ok = 4 * c < info.valid;
-      const int row0 = static_cast<int>(blockIdx.x + tl * gridDim.x) * kRows + r0;
-      float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), be = mu;
-      if ((flags & kPanelBn) && col_ok) {
-        mu = *reinterpret_cast<const float4*>(s.bn + colc);
-        sc = *reinterpret_cast<const float4*>(s.bn + k1r + colc);
-        be = *reinterpret_cast<const float4*>(s.bn + 2 * k1r + colc);
-      }
-      float4 hi[kItems], lo[kItems];
-#pragma unroll
-      for (int it = 0; it < kItems; ++it) {
-        float4 v = cur[it];
-        const int row = row0 + 32 * it;
-        const bool ok = col_ok && row < m32;
-        if (flags & kPanelBn) {
-          v.x = (v.x - mu.x) * sc.x + be.x; v.y = (v.y - mu.y) * sc.y + be.y;
-          v.z = (v.z - mu.z) * sc.z + be.z; v.w = (v.w - mu.w) * sc.w + be.w;
-        }
-        if (flags & kPanelRelu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        if ((flags & kPanelRowScale) && ok) {
-          const int deg = p.csc_ptr[row + 1] - p.csc_ptr[row];
-          const float rs = p.rowscale_mode == 2 ? static_cast<float>(deg) : (deg > 0 ? 1.f : 0.f);
-          v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
-        }
-        if (!ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
-        split_tf32(v.x, hi[it].x, lo[it].x); split_tf32(v.y, hi[it].y, lo[it].y);
-        split_tf32(v.z, hi[it].z, lo[it].z); split_tf32(v.w, hi[it].w, lo[it].w);
-      }
-      // wait until the MMAs of the previous use of this A stage have drained it
-      if (round >= 1u && !mbar_wait(&empty[stg], (round - 1u) & 1u)) timed_out = true;
-      float* dst_hi = s.a_base + stg * (2 * kABufFloats) + off0;
-      float* dst_lo = dst_hi + kABufFloats;
-#pragma unroll
-      for (int it = 0; it < kItems; ++it) {
-        *reinterpret_cast<float4*>(dst_hi + it * 1024) = hi[it];
-        *reinterpret_cast<float4*>(dst_lo + it * 1024) = lo[it];
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (MMA)
-      mbar_arrive(&full[stg]);
-#pragma unroll
-      for (int it = 0; it < kItems; ++it) cur[it] = nxt[it];
-      if (++stg == a_stages) { stg = 0; ++round; }
-      if (++pi == chunks_per_tile) {
+      cp_async_arrive(&raw_full[slot]);
+      if (++slot == raw_slots) { slot = 0; ++wrap; }
+      if (++pi == panels) {
         if (trace != nullptr && tid == 0 && tl < 32) trace[0 * 64 + tl * 2 + 1] = clock64();
         pi = 0; ++tl;
+        if (tl < my_tiles) tile_rows(tl);
       }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp < kEpiWarp0) {
+    // =========================== converters ===========================
+    const int grp = (warp - kLoaderWarps) >> 2;       // group 0: even panels, group 1: odd panels
+    const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
+    const int rl = quarter * 32 + lane;               // row of the tile = TMEM lane
+    const uint32_t lane_addr = tmem_d + (static_cast<uint32_t>(quarter * 32) << 16) + a_col0;
+    const int k1r = (p.k1 + 3) & ~3;
+    const float* rawrow = s.raw + rl * 32;
+    const int sw = rl & 7;
+    for (int g = grp; g < total; g += 2) {
+      const int tl = g / panels, pi = g - tl * panels;
+      const int slot = g % raw_slots, stg = g % a_stages;
+      const uint32_t raw_round = static_cast<uint32_t>(g / raw_slots), a_round = static_cast<uint32_t>(g / a_stages);
+      const PanelInfo& info = s.panel[pi];
+      const int flags = info.flags;
+      const int row = static_cast<int>(blockIdx.x + static_cast<int64_t>(tl) * gridDim.x) * kRows + rl;
+      const bool row_ok = row < m32;
+      float rs = 1.f;
+      if ((flags & kPanelRowScale) && row_ok) {
+        const int deg = p.csc_ptr[row + 1] - p.csc_ptr[row];
+        rs = p.rowscale_mode == 2 ? static_cast<float>(deg) : (deg > 0 ? 1.f : 0.f);
+      }
+      if (trace != nullptr && tid == kLoaderThreads && g < 30) trace[3 * 64 + 2 + (g >> 1) * 4] = clock64();
+      if (!mbar_wait(&raw_full[slot], raw_round & 1u)) timed_out = true;
+      if (trace != nullptr && tid == kLoaderThreads && g < 30) trace[3 * 64 + 3 + (g >> 1) * 4] = clock64();
+      const float* src = rawrow + static_cast<size_t>(slot) * kABufFloats;
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(src + ((j ^ sw) << 2));
+      // the MMAs of the previous use of this TMEM stage must have drained it
+      bool waited = false;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = h * 4 + jj;
+          float4 x = v[j];
+          const int colc = info.col0 + 4 * j;
+          if (flags & kPanelBn) {
+            const bool cv = 4 * j < info.valid;
+            const float4 mu = cv ? *reinterpret_cast<const float4*>(s.bn + colc) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 sc = cv ? *reinterpret_cast<const float4*>(s.bn + k1r + colc) : mu;
+            const float4 be = cv ? *reinterpret_cast<const float4*>(s.bn + 2 * k1r + colc) : mu;
+            x.x = (x.x - mu.x) * sc.x + be.x; x.y = (x.y - mu.y) * sc.y + be.y;
+            x.z = (x.z - mu.z) * sc.z + be.z; x.w = (x.w - mu.w) * sc.w + be.w;
+          }
+          if (flags & kPanelRelu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+          if (flags & kPanelRowScale) { x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs; }
+          if (!row_ok) x = make_float4(0.f, 0.f, 0.f, 0.f);   // zero-filled rows must stay zero after the affine transform
+          split_tf32(x.x, hi[jj * 4 + 0], lo[jj * 4 + 0]); split_tf32(x.y, hi[jj * 4 + 1], lo[jj * 4 + 1]);
+          split_tf32(x.z, hi[jj * 4 + 2], lo[jj * 4 + 2]); split_tf32(x.w, hi[jj * 4 + 3], lo[jj * 4 + 3]);
+        }
+        if (!waited) {
+          if (a_round >= 1u && !mbar_wait(&a_empty[stg], (a_round - 1u) & 1u)) timed_out = true;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          waited = true;
+        }
+        const uint32_t col = static_cast<uint32_t>(stg * kAStageCols + h * 16);
+        tmem_st16(lane_addr + col, hi);
+        tmem_st16(lane_addr + col + 32, lo);
+      }
+      mbar_arrive(&raw_empty[slot]);   // the panel is in registers / TMEM: the slot can be refilled
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&a_full[stg]);
+      if (trace != nullptr && tid == kLoaderThreads && g < 30) trace[3 * 64 + 4 + (g >> 1) * 4] = clock64();
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
-    // The whole warp runs this loop with uniform control flow and uniform operands (descriptors stay
-    // in uniform registers, advancing one is a 32-bit add on its low word); only the tcgen05
+    // The whole warp runs this loop with uniform control flow and uniform operands; only the tcgen05
     // instructions themselves are predicated to lane 0.  Three MMAs per k-step (hi*hi, lo*hi, hi*lo).
     const uint32_t leader = lane == 0 ? 1u : 0u;
     const uint32_t idesc = umma_idesc_tf32(kRows, np);
     const uint32_t w_panel16 = (static_cast<uint32_t>(np) * 128u) >> 4;  // one 32-float K block of W, in 16-byte units
     const uint64_t dw_hi0 = umma_desc(smem_u32(s.w_hi)), dw_lo0 = umma_desc(smem_u32(s.w_lo));
-    const uint64_t da_hi_base = umma_desc(smem_u32(s.a_base));
-    constexpr uint32_t kStage16 = (2u * kABufFloats * 4u) >> 4, kImage16 = (kABufFloats * 4u) >> 4;  // 16-byte units
     int stg = 0;
     uint32_t round = 0;
     for (int64_t tl = 0; tl < my_tiles; ++tl) {
@@ -459,23 +471,23 @@ node_gemm_kernel(TcGemmParams p) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_addr = tmem_d + static_cast<uint32_t>(ab * np);
       if (trace != nullptr && lane == 0 && tl < 32) trace[1 * 64 + tl * 2] = clock64();
-      for (int kc = 0; kc < chunks_per_tile; ++kc) {
+      for (int kc = 0; kc < panels; ++kc) {
         const int ksteps = s.panel[kc].ksteps;
-        if (!mbar_wait(&full[stg], round & 1u)) timed_out = true;
+        if (!mbar_wait(&a_full[stg], round & 1u)) timed_out = true;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t a_hi = da_hi_base + static_cast<uint64_t>(static_cast<uint32_t>(stg) * kStage16);
-        const uint64_t a_lo = a_hi + kImage16;
+        const uint32_t a_hi = tmem_d + a_col0 + static_cast<uint32_t>(stg * kAStageCols);
+        const uint32_t a_lo = a_hi + 32u;
         const uint64_t w_hi = dw_hi0 + static_cast<uint64_t>(static_cast<uint32_t>(kc) * w_panel16);
         const uint64_t w_lo = dw_lo0 + static_cast<uint64_t>(static_cast<uint32_t>(kc) * w_panel16);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {  // a k-step is 32 bytes = 2 descriptor units further into the panel
+        for (int jj = 0; jj < 4; ++jj) {  // a k-step is 8 TMEM columns of A and 32 bytes = 2 descriptor units of W
           if (jj < ksteps) {
-            umma_tf32_pred(d_addr, a_hi + 2 * jj, w_hi + 2 * jj, idesc, (kc > 0 || jj > 0) ? 1u : 0u, leader);
-            umma_tf32_pred(d_addr, a_lo + 2 * jj, w_hi + 2 * jj, idesc, 1u, leader);
-            umma_tf32_pred(d_addr, a_hi + 2 * jj, w_lo + 2 * jj, idesc, 1u, leader);
+            umma_tf32_ts_pred(d_addr, a_hi + 8 * jj, w_hi + 2 * jj, idesc, (kc > 0 || jj > 0) ? 1u : 0u, leader);
+            umma_tf32_ts_pred(d_addr, a_lo + 8 * jj, w_hi + 2 * jj, idesc, 1u, leader);
+            umma_tf32_ts_pred(d_addr, a_hi + 8 * jj, w_lo + 2 * jj, idesc, 1u, leader);
           }
         }
-        umma_commit_pred(&empty[stg], leader);   // arrives when the MMAs above have finished reading the stage
+        umma_commit_pred(&a_empty[stg], leader);   // arrives when the MMAs above have finished reading the stage
         if (++stg == a_stages) { stg = 0; ++round; }
       }
       umma_commit_pred(&acc_full[ab], leader);  // ... and when the whole tile's accumulator is complete
@@ -656,17 +668,24 @@ node_gemm_kernel(TcGemmParams p) {
   }
 }
 
-size_t smem_bytes_for(int np, int kp, int a_stages, int staged = 0) {
+size_t smem_bytes_for(int np, int kp, int raw_slots, int staged = 0) {
   const size_t kp32 = (static_cast<size_t>(kp) + 31) & ~static_cast<size_t>(31);
-  return sizeof(float) * (2 * np * kp32 + 2 * a_stages * kABufFloats + 16 * np + np + 3 * kp32 + 32 + 4 +
-                          (staged ? kStageFloats : 0)) + kMaxPanels * sizeof(PanelInfo) + 64;
+  return sizeof(float) * (2 * np * kp32 + static_cast<size_t>(raw_slots) * kABufFloats + 16 * np + np + 3 * kp32 +
+                          2 * kBarCount + 4 + (staged ? kStageFloats : 0)) + kMaxPanels * sizeof(PanelInfo) + 64;
 }
 
-int pick_a_stages(int np, int kp) {
-  if (2 * np > 512) return 0;  // two TMEM accumulators
+// TMEM: two accumulators of np columns + A stages of 64 columns each
+int pick_a_stages(int np) {
+  const int st = (512 - 2 * np) / kAStageCols;
+  return st > kMaxAStages ? kMaxAStages : st;
+}
+
+// raw ring slots that fit beside W (0: the contraction does not fit this kernel)
+int pick_raw_slots(int np, int kp, int staged) {
+  if (pick_a_stages(np) < 1) return 0;
   if (kp > kMaxPanels * kKc) return 0;
-  for (int st = kMaxStages; st >= 1; --st)
-    if (smem_bytes_for(np, kp, st) <= 227 * 1024) return st;
+  for (int sl = kMaxRaw; sl >= 2; --sl)
+    if (smem_bytes_for(np, kp, sl, staged) <= 227 * 1024) return sl;
   return 0;
 }
 
@@ -683,7 +702,7 @@ bool tc_gemm_supported(const TcGemmShape& sh) {
   if (sh.kt % 4 != 0) return false;
   const int np = tc_padded_n(sh.n), kp = tc_padded_k(sh);
   if (np > 256) return false;
-  return pick_a_stages(np, kp) > 0;
+  return pick_raw_slots(np, kp, 0) > 0;
 }
 
 size_t tc_pack_floats(const TcGemmShape& sh) {
@@ -706,32 +725,34 @@ int tc_pack_weights(const TcWeightBlocks& blocks, const TcGemmShape& sh, float* 
   return RGNN_OK;
 }
 
-// debug: device buffer of 4 * 64 int64 receiving CTA 0's timeline of the NEXT launch whose tag matches
+// debug: device buffer of 4 * 64 int64 receiving CTA 0's timeline of a later launch whose tag matches;
+// "tag@k" skips the first k matching launches (k-th layer of a fused forward)
 static long long* g_trace_buffer = nullptr;
 static char g_trace_tag[64] = "";
+static int g_trace_skip = 0;
 extern "C" void rgnn_debug_trace_node_gemm(void* device_buffer, const char* tag) {
   g_trace_buffer = static_cast<long long*>(device_buffer);
   snprintf(g_trace_tag, sizeof(g_trace_tag), "%s", tag != nullptr ? tag : "");
+  g_trace_skip = 0;
+  char* at = strchr(g_trace_tag, '@');
+  if (at != nullptr) { g_trace_skip = atoi(at + 1); *at = 0; }
 }
 
 int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
   if (p.m <= 0) return RGNN_OK;
-  if (g_trace_buffer != nullptr && strcmp(tag, g_trace_tag) == 0) { p.trace = g_trace_buffer; g_trace_buffer = nullptr; }
+  if (g_trace_buffer != nullptr && strcmp(tag, g_trace_tag) == 0 && g_trace_skip-- <= 0) { p.trace = g_trace_buffer; g_trace_buffer = nullptr; }
   p.np = tc_padded_n(p.n);
   p.kp = tc_seg_pad(p.k1) + tc_seg_pad(p.k2) + tc_seg_pad(p.kt) + tc_seg_pad(p.k3);
   if (p.n_store < p.n) p.n_store = p.n;
-  p.a_stages = pick_a_stages(p.np, p.kp);
-  if (p.a_stages == 0) return RGNN_ERR_UNSUPPORTED;
+  p.a_stages = pick_a_stages(p.np);
   // coalesced (staged) epilogue when there is neither residual nor BatchNorm sums, the rows allow
-  // 16-byte stores and the transpose buffers still fit
-  p.staged_epilogue = (p.residual == nullptr && p.bn_partial == nullptr && (p.ldy & 3) == 0 && (p.n_store & 3) == 0) ? 1 : 0;
-  if (p.staged_epilogue) {
-    // the transpose buffers may cost one A stage
-    while (p.a_stages > 1 && smem_bytes_for(p.np, p.kp, p.a_stages, 1) > 227 * 1024) --p.a_stages;
-    if (smem_bytes_for(p.np, p.kp, p.a_stages, 1) > 227 * 1024) p.staged_epilogue = 0;
-  }
+  // 16-byte stores and the transpose buffers still leave room for the raw ring
+  p.staged_epilogue = (p.residual == nullptr && p.bn_partial == nullptr && (p.ldy & 3) == 0 && (p.n_store & 3) == 0 &&
+                       pick_raw_slots(p.np, p.kp, 1) >= 2) ? 1 : 0;
+  p.raw_slots = pick_raw_slots(p.np, p.kp, p.staged_epilogue);
+  if (p.raw_slots < 2 || p.a_stages < 1) return RGNN_ERR_UNSUPPORTED;
   if (p.y2 != nullptr && (!p.staged_epilogue || (p.n_split & 3) != 0 || (p.ldy2 & 3) != 0)) return RGNN_ERR_UNSUPPORTED;
-  const size_t smem = smem_bytes_for(p.np, p.kp, p.a_stages, p.staged_epilogue);
+  const size_t smem = smem_bytes_for(p.np, p.kp, p.raw_slots, p.staged_epilogue);
   static size_t configured = 0;
   if (smem > configured) {
     RGNN_CUDA_CHECK(cudaFuncSetAttribute(node_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -14,7 +14,7 @@ x0 = torch.from_numpy(synthetic.node_embeddings(n, 64)).cuda()
 cfg = make_cfg()
 for _ in range(3):
     ops.pipeline_forward(cfg, pos, vel, x0)
-for tag in (b"node_gemm_pre", b"node_gemm_post"):
+for tag in (b"node_gemm_pre", b"node_gemm_post", b"node_gemm_pre@2", b"node_gemm_post@2"):
     buf = torch.zeros(4 * 64, dtype=torch.int64, device="cuda")
     fn(buf.data_ptr(), tag)
     ops.pipeline_forward(cfg, pos, vel, x0)
@@ -22,7 +22,12 @@ for tag in (b"node_gemm_pre", b"node_gemm_post"):
     t = buf.cpu().numpy().reshape(4, 32, 2)
     t0 = t[3, 0, 0]
     print(tag.decode(), "kernel cycles (CTA 0):", t[3, 0, 1] - t0)
+    tag = tag.split(b"@")[0]
     for tl in range(8):
         if t[0, tl, 0] == 0: break
         row = [int(v - t0) for v in (t[0, tl, 0], t[0, tl, 1], t[1, tl, 0], t[1, tl, 1], t[2, tl, 0], t[2, tl, 1])]
-        print(f"  tile {tl}: producer {row[0]:7d}..{row[1]:7d}  mma {row[2]:7d}..{row[3]:7d}  epilogue {row[4]:7d}..{row[5]:7d}")
+        print(f"  tile {tl}: loader {row[0]:7d}..{row[1]:7d}  mma {row[2]:7d}..{row[3]:7d}  epilogue {row[4]:7d}..{row[5]:7d}")
+    f = buf.cpu().numpy()[3 * 64 + 2: 3 * 64 + 62].reshape(15, 4)
+    for g in range(15):
+        if f[g, 0] == 0: break
+        print(f"  converter panel {2*g:2d}: start {int(f[g,0]-t0):7d}  raw-wait {int(f[g,1]-f[g,0]):6d}  convert+st {int(f[g,2]-f[g,1]):6d}")
