@@ -260,23 +260,20 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane & 7, quarter = lane >> 3;
-  float4 w[DE][4], wt[DE];
+  float4 wt[DE];
 #pragma unroll
-  for (int d = 0; d < DE; ++d) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) w[d][i] = ld4(&ws[d][32 * i + 4 * q]);
-    wt[d] = ld4(&ws[d][kSplitMain]);
-  }
+  for (int d = 0; d < DE; ++d) wt[d] = ld4(&ws[d][kSplitMain]);
   constexpr float kInit = MODE == RGNN_AGGR_MAX ? -INFINITY : (MODE == RGNN_AGGR_MIN ? INFINITY : 0.f);
   const float4 init4 = make_float4(kInit, kInit, kInit, kInit);
   const float* bcol = bm + 4 * q;
   constexpr int kPasses = kSplitRows / 16;
+  constexpr int kHold = 4;                       // slots held per lane: a quarter holds 8 * kHold = 32 slots of its row
   const int row_base = blockIdx.x * kSplitRows + warp * 4 + quarter;
 
-  // Software pipeline over the passes: the row pointers run two passes ahead and the first 16 slots
-  // (lane q holds slots q and q + 8: source index, edge attributes) one pass ahead, so that a pass starts
-  // its gathers without waiting for an index load.
-  struct SlotRegs { int src[2]; float e[2][DE]; };
+  // Software pipeline over the passes: the row pointers run two passes ahead and the first 32 slots
+  // (lane q holds slots q, q + 8, q + 16, q + 24: source index, edge attributes) one pass ahead, so that
+  // a pass starts its gathers without waiting for an index load.
+  struct SlotRegs { int src[kHold]; float e[kHold][DE]; };
   auto load_ptr = [&](int pass, int& beg, int& deg) {
     const int row = row_base + pass * 16;
     beg = 0; deg = 0;
@@ -284,7 +281,7 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
   };
   auto load_slots = [&](int beg, int deg, int b, SlotRegs& r) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kHold; ++h) {
       r.src[h] = 0;
 #pragma unroll
       for (int d = 0; d < DE; ++d) r.e[h][d] = 0.f;
@@ -312,24 +309,22 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
     const int nmax = __reduce_max_sync(0xffffffffu, deg);
     float4 acc[4] = {init4, init4, init4, init4};
     float4 tacc = init4;
-    for (int b = 0; b < nmax; b += 16) {
-      if (b > 0) load_slots(beg, deg, b, cur);   // in-degree above 16: not prefetched
-      // tail channels, slot-parallel
+    for (int b = 0; b < nmax; b += 8 * kHold) {
+      if (b > 0) load_slots(beg, deg, b, cur);   // in-degree above 32: not prefetched
+      // tail channels, slot-parallel: issue the narrow gathers now, use them after the first main group
+      float4 tl[kHold];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (b + 8 * h + q < deg) {
-          float4 t = ld4(bt + static_cast<int64_t>(cur.src[h]) * 4);
+      for (int h = 0; h < kHold; ++h)
+        tl[h] = (b + 8 * h + q < deg) ? ld4(bt + static_cast<int64_t>(cur.src[h]) * 4) : init4;
 #pragma unroll
-          for (int d = 0; d < DE; ++d) t = fma4(cur.e[h][d], wt[d], t);
-          tacc = combine4<MODE>(tacc, t);
-        }
-      }
-      for (int g = 0; g < 4; ++g) {
-        if (b + 4 * g >= nmax) break;   // warp-uniform
-        const int sreg = g < 2 ? cur.src[0] : cur.src[1];
+      for (int hh = 0; hh < kHold; ++hh)
+      for (int gg = 0; gg < 2; ++gg) {
+        const int g = 2 * hh + gg;
+        if (b + 4 * g >= nmax) break;   // warp-uniform (a later hh iteration breaks again right away)
+        const int sreg = cur.src[hh];
         float ereg[DE];
 #pragma unroll
-        for (int d = 0; d < DE; ++d) ereg[d] = g < 2 ? cur.e[0][d] : cur.e[1][d];
+        for (int d = 0; d < DE; ++d) ereg[d] = cur.e[hh][d];
         const int l0 = (4 * g) & 7;
         float4 v[4][4];
 #pragma unroll
@@ -340,19 +335,35 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
 #pragma unroll
           for (int i = 0; i < 4; ++i) v[u][i] = on ? ld4(rp + 32 * i) : init4;
         }
+        float ed[4][DE];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
-          for (int d = 0; d < DE; ++d) {
-            const float ed = __shfl_sync(0xffffffffu, ereg[d], l0 + u, 8);   // 0 for slots beyond the row's degree
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[u][i] = fma4x2(ed, w[d][i], v[u][i]);
-          }
-        }
+          for (int d = 0; d < DE; ++d) ed[u][d] = __shfl_sync(0xffffffffu, ereg[d], l0 + u, 8);   // 0 beyond the row's degree
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          // the edge weights of this lane's channels come from shared memory chunk by chunk (registers
+          // are the occupancy limit of this kernel)
+          float4 wi[DE];
+#pragma unroll
+          for (int d = 0; d < DE; ++d) wi[d] = ld4(&ws[d][32 * i + 4 * q]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int d = 0; d < DE; ++d) v[u][i] = fma4x2(ed[u][d], wi[d], v[u][i]);
           acc[i] = combine4x2<MODE>(acc[i], v[0][i], v[1][i]);
           acc[i] = combine4x2<MODE>(acc[i], v[2][i], v[3][i]);
+        }
+        if (g == 0) {
+#pragma unroll
+          for (int h = 0; h < kHold; ++h) {
+            if (b + 8 * h + q < deg) {
+              float4 t = tl[h];
+#pragma unroll
+              for (int d = 0; d < DE; ++d) t = fma4(cur.e[h][d], wt[d], t);
+              tacc = combine4<MODE>(tacc, t);
+            }
+          }
         }
       }
     }

@@ -101,6 +101,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
   lo = v - hi;  // exact
@@ -396,10 +408,12 @@ node_gemm_kernel(TcGemmParams p) {
     const int k1r = (p.k1 + 3) & ~3;
     const float* rawrow = s.raw + rl * 32;
     const int sw = rl & 7;
+    // (tile, panel), ring slot and TMEM stage of panel g, advanced by two panels per iteration
+    int tl = 0, pi = grp, slot = grp, stg = grp;
+    uint32_t raw_round = 0, a_round = 0;
+    while (pi >= panels) { pi -= panels; ++tl; }
+    while (stg >= a_stages) { stg -= a_stages; ++a_round; }
     for (int g = grp; g < total; g += 2) {
-      const int tl = g / panels, pi = g - tl * panels;
-      const int slot = g % raw_slots, stg = g % a_stages;
-      const uint32_t raw_round = static_cast<uint32_t>(g / raw_slots), a_round = static_cast<uint32_t>(g / a_stages);
       const PanelInfo& info = s.panel[pi];
       const int flags = info.flags;
       const int row = static_cast<int>(blockIdx.x + static_cast<int64_t>(tl) * gridDim.x) * kRows + rl;
@@ -454,6 +468,9 @@ node_gemm_kernel(TcGemmParams p) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&a_full[stg]);
       if (trace != nullptr && tid == kLoaderThreads && g < 30) trace[3 * 64 + 4 + (g >> 1) * 4] = clock64();
+      pi += 2; while (pi >= panels) { pi -= panels; ++tl; }
+      slot += 2; if (slot >= raw_slots) { slot -= raw_slots; ++raw_round; }
+      stg += 2; while (stg >= a_stages) { stg -= a_stages; ++a_round; }
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
@@ -519,50 +536,49 @@ node_gemm_kernel(TcGemmParams p) {
         // Coalesced path (no residual / BatchNorm sums): 32 columns at a time through a per-warp
         // transpose buffer, so that a store instruction writes 4 rows x 128 contiguous bytes instead
         // of 32 rows x 16 bytes (8x fewer LSU wavefronts; the strided form bounded the kernel).
+        // Padding columns need no masking: their W rows and bias entries are zero, so the accumulator
+        // holds exact zeros there.  Everything that does not depend on the row is hoisted out of the
+        // store loop -- the epilogue is a serial chain on two warps per scheduler, instruction count is
+        // what bounds it.
         float* st = s.stage + ew * (32 * 36);
         const int n_dbl = (n_blocks + 1) >> 1;
         const int n_split = p.y2 != nullptr ? p.n_split : 0x7fffffff;
         const int64_t tile_row0 = tile * kRows + q * 32;
+        const int rows_valid = static_cast<int>(p.m - tile_row0 < 32 ? p.m - tile_row0 : 32);
+        const int c4 = lane & 7, rsub = lane >> 3;
         for (int cd = half; cd < n_dbl; cd += 2) {
-          uint32_t r0[16], r1[16];
           const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ab * np + cd * 32);
-          const bool second = cd * 2 + 1 < n_blocks;
-          tmem_ld16(taddr, r0);
-          if (second) tmem_ld16(taddr + 16, r1);
+          float* strow = st + lane * 36;
+          if (cd * 2 + 1 < n_blocks) {
+            uint32_t r[32];
+            tmem_ld32(taddr, r);
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 bv = *reinterpret_cast<const float4*>(s.bias + cd * 32 + j4 * 4);
-            *reinterpret_cast<float4*>(st + lane * 36 + j4 * 4) =
-                make_float4(__uint_as_float(r0[j4 * 4]) + bv.x, __uint_as_float(r0[j4 * 4 + 1]) + bv.y,
-                            __uint_as_float(r0[j4 * 4 + 2]) + bv.z, __uint_as_float(r0[j4 * 4 + 3]) + bv.w);
-          }
-          if (second) {
+            for (int j4 = 0; j4 < 8; ++j4)
+              *reinterpret_cast<uint4*>(strow + j4 * 4) = make_uint4(r[j4 * 4], r[j4 * 4 + 1], r[j4 * 4 + 2], r[j4 * 4 + 3]);
+          } else {
+            uint32_t r[16];
+            tmem_ld16(taddr, r);
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 bv = *reinterpret_cast<const float4*>(s.bias + cd * 32 + 16 + j4 * 4);
-              *reinterpret_cast<float4*>(st + lane * 36 + 16 + j4 * 4) =
-                  make_float4(__uint_as_float(r1[j4 * 4]) + bv.x, __uint_as_float(r1[j4 * 4 + 1]) + bv.y,
-                              __uint_as_float(r1[j4 * 4 + 2]) + bv.z, __uint_as_float(r1[j4 * 4 + 3]) + bv.w);
-            }
+            for (int j4 = 0; j4 < 4; ++j4)
+              *reinterpret_cast<uint4*>(strow + j4 * 4) = make_uint4(r[j4 * 4], r[j4 * 4 + 1], r[j4 * 4 + 2], r[j4 * 4 + 3]);
           }
           __syncwarp();
-          const int c4 = lane & 7, rsub = lane >> 3;
           const int col = cd * 32 + c4 * 4;
+          if (col < p.n_store && col < np) {
+            const float4 bv = *reinterpret_cast<const float4*>(s.bias + col);
+            // split output: columns from n_split on go to the narrow tail array y2
+            float* dst;
+            int64_t ld;
+            if (col < n_split) { ld = p.ldy; dst = p.y + (tile_row0 + rsub) * ld + col; }
+            else { ld = p.ldy2; dst = p.y2 + (tile_row0 + rsub) * ld + (col - n_split); }
+            const float* srow = st + rsub * 36 + c4 * 4;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rl = it * 4 + rsub;
-            const int64_t grow = tile_row0 + rl;
-            if (grow < p.m && col < p.n_store) {
-              float4 v4 = *reinterpret_cast<const float4*>(st + rl * 36 + c4 * 4);
-              if (col + 3 >= p.n) {  // padding columns are written as exact zeros
-                if (col + 0 >= p.n) v4.x = 0.f;
-                if (col + 1 >= p.n) v4.y = 0.f;
-                if (col + 2 >= p.n) v4.z = 0.f;
-                if (col + 3 >= p.n) v4.w = 0.f;
+            for (int it = 0; it < 8; ++it) {
+              if (it * 4 + rsub < rows_valid) {
+                float4 v4 = *reinterpret_cast<const float4*>(srow + it * (4 * 36));
+                v4.x += bv.x; v4.y += bv.y; v4.z += bv.z; v4.w += bv.w;
+                *reinterpret_cast<float4*>(dst + it * 4 * ld) = v4;
               }
-              // split output: columns from n_split on go to the narrow tail array y2
-              if (col < n_split) *reinterpret_cast<float4*>(p.y + grow * p.ldy + col) = v4;
-              else *reinterpret_cast<float4*>(p.y2 + grow * p.ldy2 + (col - n_split)) = v4;
             }
           }
           __syncwarp();

@@ -19,7 +19,7 @@ __host__ __device__ constexpr uint32_t idesc(int fmt, int m, int n) {
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-template <int KIND>  // 0 = tf32, 1 = bf16
+template <int KIND>  // 0 = tf32, 1 = bf16, 2 = tf32 with the A operand in tensor memory
 __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int distinct, long long* out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar;
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int dist
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(256) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -43,14 +43,18 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int dist
     // warp-uniform issue loop (descriptors in uniform registers), lane 0 issues; 16 MMAs per iteration
     const uint32_t leader = (tid == 0) ? 1u : 0u;
     const uint64_t da0 = umma_desc(smem_u32(smem)), db0 = umma_desc(smem_u32(smem + 64 * 1024));
-    const uint32_t id = idesc(KIND == 0 ? 2 : 1, 128, n);
+    const uint32_t id = idesc(KIND == 1 ? 1 : 2, 128, n);
     const long long t0 = clock64();
     for (int i = 0; i < iters; i += 16) {
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const uint64_t da = da0 + 2 * (u & 3) * (distinct > 1 ? 1 : 0);
         const uint64_t db = db0 + 2 * (u & 3) * (distinct > 1 ? 1 : 0);
-        if (KIND == 0) {
+        if (KIND == 2) {
+          const uint32_t ta = tmem_d + 256u + 8u * (u & 3) * (distinct > 1 ? 1 : 0);
+          asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                       ::"r"(tmem_d), "r"(ta), "l"(db), "r"(id), "r"(1u), "r"(leader) : "memory");
+        } else if (KIND == 0) {
           asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
                        ::"r"(tmem_d), "l"(da), "l"(db), "r"(id), "r"(1u), "r"(leader) : "memory");
         } else {
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int dist
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512) : "memory");
 }
 
 int main() {
@@ -81,18 +85,20 @@ int main() {
   const size_t smem = 192 * 1024;
   cudaFuncSetAttribute(rate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int iters = 2048;
-  for (int kind = 0; kind < 2; ++kind)
+  for (int kind = 0; kind < 3; ++kind)
     for (int grid : {1, 148})
       for (int n : {16, 64, 128, 144, 256})
         for (int distinct : {1, 4}) {
           for (int rep = 0; rep < 2; ++rep) {
             if (kind == 0) rate_kernel<0><<<grid, 128, smem>>>(n, iters, distinct, out);
-            else rate_kernel<1><<<grid, 128, smem>>>(n, iters, distinct, out);
+            else if (kind == 1) rate_kernel<1><<<grid, 128, smem>>>(n, iters, distinct, out);
+            else rate_kernel<2><<<grid, 128, smem>>>(n, iters, distinct, out);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
           }
-          printf("kind=%s grid=%3d N=%3d distinct=%d: issue %.1f cyc/mma, complete %.1f cyc/mma\n", kind == 0 ? "tf32" : "bf16",
+          printf("kind=%s grid=%3d N=%3d distinct=%d: issue %.1f cyc/mma, complete %.1f cyc/mma\n", kind == 0 ? "tf32" : (kind == 1 ? "bf16" : "tf32-TS"),
                  grid, n, distinct, (double)out[0] / iters, (double)out[1] / iters);
         }
   return 0;
