@@ -260,13 +260,18 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane & 7, quarter = lane >> 3;
-  float4 wt[DE];
+  float4 w[DE][4], wt[DE];
 #pragma unroll
-  for (int d = 0; d < DE; ++d) wt[d] = ld4(&ws[d][kSplitMain]);
+  for (int d = 0; d < DE; ++d) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[d][i] = ld4(&ws[d][32 * i + 4 * q]);
+    wt[d] = ld4(&ws[d][kSplitMain]);
+  }
   constexpr float kInit = MODE == RGNN_AGGR_MAX ? -INFINITY : (MODE == RGNN_AGGR_MIN ? INFINITY : 0.f);
   const float4 init4 = make_float4(kInit, kInit, kInit, kInit);
   const float* bcol = bm + 4 * q;
   constexpr int kPasses = kSplitRows / 16;
+  constexpr bool kOrderFree = MODE == RGNN_AGGR_MAX || MODE == RGNN_AGGR_MIN;
   constexpr int kHold = 4;                       // slots held per lane: a quarter holds 8 * kHold = 32 slots of its row
   const int row_base = blockIdx.x * kSplitRows + warp * 4 + quarter;
 
@@ -309,6 +314,11 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
     const int nmax = __reduce_max_sync(0xffffffffu, deg);
     float4 acc[4] = {init4, init4, init4, init4};
     float4 tacc = init4;
+    float4 v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[u][i] = init4;
     for (int b = 0; b < nmax; b += 8 * kHold) {
       if (b > 0) load_slots(beg, deg, b, cur);   // in-degree above 32: not prefetched
       // tail channels, slot-parallel: issue the narrow gathers now, use them after the first main group
@@ -326,31 +336,35 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
 #pragma unroll
         for (int d = 0; d < DE; ++d) ereg[d] = cur.e[hh][d];
         const int l0 = (4 * g) & 7;
-        float4 v[4][4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int sidx = __shfl_sync(0xffffffffu, sreg, l0 + u, 8);
           const bool on = b + 4 * g + u < deg;
           const float* rp = bcol + static_cast<int64_t>(sidx) * kSplitMain;
+          // max / min: a slot beyond the row's degree keeps the registers of an earlier slot of the same
+          // row (its edge attributes are zero, so the value is re-submitted unchanged: harmless);
+          // sums start every slot from zero
+          if (kOrderFree) {
+            if (on) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[u][i] = on ? ld4(rp + 32 * i) : init4;
+              for (int i = 0; i < 4; ++i) v[u][i] = ld4(rp + 32 * i);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[u][i] = on ? ld4(rp + 32 * i) : init4;
+          }
         }
-        float ed[4][DE];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u) {
 #pragma unroll
-          for (int d = 0; d < DE; ++d) ed[u][d] = __shfl_sync(0xffffffffu, ereg[d], l0 + u, 8);   // 0 beyond the row's degree
+          for (int d = 0; d < DE; ++d) {
+            const float ed = __shfl_sync(0xffffffffu, ereg[d], l0 + u, 8);   // 0 for slots beyond the row's degree
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[u][i] = fma4x2(ed, w[d][i], v[u][i]);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          // the edge weights of this lane's channels come from shared memory chunk by chunk (registers
-          // are the occupancy limit of this kernel)
-          float4 wi[DE];
-#pragma unroll
-          for (int d = 0; d < DE; ++d) wi[d] = ld4(&ws[d][32 * i + 4 * q]);
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int d = 0; d < DE; ++d) v[u][i] = fma4x2(ed[u][d], wi[d], v[u][i]);
           acc[i] = combine4x2<MODE>(acc[i], v[0][i], v[1][i]);
           acc[i] = combine4x2<MODE>(acc[i], v[2][i], v[3][i]);
         }

@@ -119,7 +119,8 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
 }
 
 // ---- weight packing ------------------------------------------------------------------------
-// image = one swizzled [np x 32] panel per 32-float K block, hi image followed by lo image
+// image = per 32-float K block one swizzled [np x 32] panel of hi parts directly followed by the panel of
+// lo parts, so that a single B descriptor with N = 2 np covers [W_hi ; W_lo] of the block
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(TcWeightBlocks blocks, int np, int kp, float* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,9 +136,9 @@ pack_weights_kernel(TcWeightBlocks blocks, int np, int kp, float* __restrict__ o
   }
   float hi, lo;
   split_tf32(v, hi, lo);
-  const int off = (kcol >> 5) * (np * 32) + sw128_offset(nrow, (kcol & 31) >> 2) + (kcol & 3);
+  const int off = (kcol >> 5) * (2 * np * 32) + sw128_offset(nrow, (kcol & 31) >> 2) + (kcol & 3);
   out[off] = hi;
-  out[np * kp + off] = lo;
+  out[np * 32 + off] = lo;
 }
 
 // w_fold[c_out, c] = W_m[c_out, p] . W_t[p, c]   (fp64 accumulate): the target-node half of the first
@@ -200,7 +201,7 @@ struct PanelInfo {
 };
 
 struct SmemLayout {
-  float* w_hi; float* w_lo;
+  float* w;                        // per K block: [np x 32] hi panel, [np x 32] lo panel (swizzled)
   float* raw;                      // [raw_slots][128 x 32] fp32 panels as loaded (row r chunk c at c ^ (r % 8))
   float* col_sum;                  // [2 accumulators][4 quarters][np]
   float* col_sq;
@@ -208,18 +209,17 @@ struct SmemLayout {
   float* bn;                       // [3][k1] mean | scale | beta of the a1 transform
   float* stage;                    // optional: 8 epilogue warps x [32][36] transpose buffers (coalesced stores)
   PanelInfo* panel;                // [kMaxPanels]
-  uint64_t* bar;                   // raw_full[6], raw_empty[6], a_full[4], a_empty[4], acc_full[2], acc_empty[2]
+  uint64_t* bar;                   // raw_full[6], raw_empty[6], a_full[4], a_empty[4], acc_full[2], acc_empty[2], setup
   uint32_t* tmem_base;
 };
 
 constexpr int kStageFloats = 8 * 32 * 36;
-constexpr int kBarCount = 2 * kMaxRaw + 2 * kMaxAStages + 4;
+constexpr int kBarCount = 2 * kMaxRaw + 2 * kMaxAStages + 5;
 
 __device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int np, int kp32, int raw_slots, int k1, int staged) {
   SmemLayout s;
   float* f = reinterpret_cast<float*>(base);
-  s.w_hi = f; f += static_cast<size_t>(np) * kp32;
-  s.w_lo = f; f += static_cast<size_t>(np) * kp32;
+  s.w = f; f += 2 * static_cast<size_t>(np) * kp32;
   s.raw = f; f += static_cast<size_t>(raw_slots) * kABufFloats;
   s.col_sum = f; f += 8 * np;
   s.col_sq = f; f += 8 * np;
@@ -284,12 +284,19 @@ node_gemm_kernel(TcGemmParams p) {
   uint64_t* acc_full = a_empty + kMaxAStages;          // [2]
   uint64_t* acc_empty = acc_full + 2;                  // [2]
 
-  // ---- one-time setup: barriers, TMEM, resident weights, bias, BatchNorm-on-load parameters ------
+  uint64_t* setup_bar = acc_empty + 2;
+  const bool dual = p.dual != 0;   // one MMA per k-step for hi*hi and hi*lo: N = 2 np against [W_hi ; W_lo]
+  const int acc_stride = dual ? 2 * np : np;   // TMEM columns of one accumulator
+
+  // ---- one-time setup, part 1 (no global loads): barriers, TMEM, panel table ----------------------
+  long long t_entry = 0;
+  if (p.trace != nullptr && blockIdx.x == 0 && tid == 0) t_entry = clock64();
   if (tid == 0) {
     for (int i = 0; i < kMaxRaw; ++i) { mbar_init(&raw_full[i], kLoaderThreads); mbar_init(&raw_empty[i], kConvGroupThreads); }
     for (int i = 0; i < kMaxAStages; ++i) { mbar_init(&a_full[i], kConvGroupThreads); mbar_init(&a_empty[i], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_init(&acc_empty[0], kEpilogueThreads); mbar_init(&acc_empty[1], kEpilogueThreads);
+    mbar_init(setup_bar, kEpilogueThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
@@ -298,48 +305,32 @@ node_gemm_kernel(TcGemmParams p) {
   }
   const int k1p = (p.k1 + 31) & ~31, k2p = (p.k2 + 31) & ~31, ktp = (p.kt + 31) & ~31;
   const int panels = (kp + kKc - 1) / kKc;
-  {
-    // resident weights: fire-and-forget cp.async (no register staging), waited for before the barrier
-    const int total16 = (2 * np * kp32) >> 2;
-    const uint32_t w_addr = smem_u32(s.w_hi);
-    for (int i = tid; i < total16; i += kGemmThreads) cp_async16(w_addr + i * 16u, p.wpack + i * 4, 16);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int i = tid; i < np; i += kGemmThreads) s.bias[i] = (p.bias != nullptr && i < p.n) ? p.bias[i] : 0.f;
-    if (p.a1_mean != nullptr) {
-      const int k1r = (p.k1 + 3) & ~3;
-      for (int i = tid; i < p.k1; i += kGemmThreads) {
-        s.bn[i] = p.a1_mean[i]; s.bn[k1r + i] = p.a1_scale[i]; s.bn[2 * k1r + i] = p.a1_beta[i];
-      }
+  if (tid < panels && tid < kMaxPanels) {
+    // which segment panel `tid` lies in
+    const int k0 = tid * kKc;
+    PanelInfo pi;
+    const int a1_flags = (p.a1_mean != nullptr ? kPanelBn : 0) | (p.relu_a1 ? kPanelRelu : 0) |
+                         (p.a1_rows != nullptr ? kPanelGather : 0);
+    if (k0 < k1p) {
+      pi.base = p.a1; pi.ld = p.lda1; pi.col0 = k0; pi.valid = min(32, p.k1 - k0); pi.flags = a1_flags;
+    } else if (k0 < k1p + k2p) {
+      pi.base = p.a2; pi.ld = p.lda2; pi.col0 = k0 - k1p; pi.valid = min(32, p.k2 - pi.col0);
+      pi.flags = p.relu_a2 ? kPanelRelu : 0;
+    } else if (k0 < k1p + k2p + ktp) {
+      pi.base = p.at; pi.ld = p.ldat; pi.col0 = k0 - k1p - k2p; pi.valid = min(32, p.kt - pi.col0);
+      pi.flags = p.relu_a2 ? kPanelRelu : 0;
+    } else {
+      pi.base = p.a1; pi.ld = p.lda1; pi.col0 = k0 - k1p - k2p - ktp; pi.valid = min(32, p.k3 - pi.col0);
+      pi.flags = a1_flags | kPanelRowScale;
     }
-    if (tid < panels && tid < kMaxPanels) {
-      // which segment panel `tid` lies in
-      const int k0 = tid * kKc;
-      PanelInfo pi;
-      const int a1_flags = (p.a1_mean != nullptr ? kPanelBn : 0) | (p.relu_a1 ? kPanelRelu : 0) |
-                           (p.a1_rows != nullptr ? kPanelGather : 0);
-      if (k0 < k1p) {
-        pi.base = p.a1; pi.ld = p.lda1; pi.col0 = k0; pi.valid = min(32, p.k1 - k0); pi.flags = a1_flags;
-      } else if (k0 < k1p + k2p) {
-        pi.base = p.a2; pi.ld = p.lda2; pi.col0 = k0 - k1p; pi.valid = min(32, p.k2 - pi.col0);
-        pi.flags = p.relu_a2 ? kPanelRelu : 0;
-      } else if (k0 < k1p + k2p + ktp) {
-        pi.base = p.at; pi.ld = p.ldat; pi.col0 = k0 - k1p - k2p; pi.valid = min(32, p.kt - pi.col0);
-        pi.flags = p.relu_a2 ? kPanelRelu : 0;
-      } else {
-        pi.base = p.a1; pi.ld = p.lda1; pi.col0 = k0 - k1p - k2p - ktp; pi.valid = min(32, p.k3 - pi.col0);
-        pi.flags = a1_flags | kPanelRowScale;
-      }
-      pi.ksteps = (pi.valid + 7) >> 3;
-      s.panel[tid] = pi;
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    pi.ksteps = (pi.valid + 7) >> 3;
+    s.panel[tid] = pi;
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // W: generic-proxy writes -> async proxy (MMA)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *s.tmem_base;
-  const uint32_t a_col0 = static_cast<uint32_t>(2 * np);   // A stages follow the two accumulators
+  const uint32_t a_col0 = static_cast<uint32_t>(2 * acc_stride);   // A stages follow the two accumulators
 
   const int64_t n_tiles = (p.m + kRows - 1) / kRows;
   const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -348,7 +339,7 @@ node_gemm_kernel(TcGemmParams p) {
   bool timed_out = false;
   // optional timeline of CTA 0 (debug): trace[role * 64 + tile * 2 + {0, 1}] = clock64
   long long* trace = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
-  if (trace != nullptr && tid == 0) trace[3 * 64] = clock64();
+  if (trace != nullptr && tid == 0) { trace[3 * 64] = clock64(); trace[3 * 64 + 63] = t_entry; }
 
   if (warp < kLoaderWarps) {
     // =========================== loaders ===========================
@@ -408,6 +399,7 @@ node_gemm_kernel(TcGemmParams p) {
     const int k1r = (p.k1 + 3) & ~3;
     const float* rawrow = s.raw + rl * 32;
     const int sw = rl & 7;
+    if (!mbar_wait(setup_bar, 0u)) timed_out = true;   // BatchNorm-on-load parameters are in shared memory
     // (tile, panel), ring slot and TMEM stage of panel g, advanced by two panels per iteration
     int tl = 0, pi = grp, slot = grp, stg = grp;
     uint32_t raw_round = 0, a_round = 0;
@@ -478,15 +470,19 @@ node_gemm_kernel(TcGemmParams p) {
     // instructions themselves are predicated to lane 0.  Three MMAs per k-step (hi*hi, lo*hi, hi*lo).
     const uint32_t leader = lane == 0 ? 1u : 0u;
     const uint32_t idesc = umma_idesc_tf32(kRows, np);
-    const uint32_t w_panel16 = (static_cast<uint32_t>(np) * 128u) >> 4;  // one 32-float K block of W, in 16-byte units
-    const uint64_t dw_hi0 = umma_desc(smem_u32(s.w_hi)), dw_lo0 = umma_desc(smem_u32(s.w_lo));
+    const uint32_t idesc2 = umma_idesc_tf32(kRows, dual ? 2 * np : np);
+    const uint32_t w_block16 = (2u * static_cast<uint32_t>(np) * 128u) >> 4;  // one K block of W (hi + lo panels), 16-byte units
+    const uint32_t w_lo16 = (static_cast<uint32_t>(np) * 128u) >> 4;          // hi panel -> lo panel
+    const uint64_t dw0 = umma_desc(smem_u32(s.w));
     int stg = 0;
     uint32_t round = 0;
+    if (!mbar_wait(setup_bar, 0u)) timed_out = true;   // W is resident
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int64_t tl = 0; tl < my_tiles; ++tl) {
       const int ab = static_cast<int>(tl & 1);
       if (tl >= 2 && !mbar_wait(&acc_empty[ab], static_cast<uint32_t>(((tl >> 1) - 1) & 1))) timed_out = true;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d_addr = tmem_d + static_cast<uint32_t>(ab * np);
+      const uint32_t d_addr = tmem_d + static_cast<uint32_t>(ab * acc_stride);
       if (trace != nullptr && lane == 0 && tl < 32) trace[1 * 64 + tl * 2] = clock64();
       for (int kc = 0; kc < panels; ++kc) {
         const int ksteps = s.panel[kc].ksteps;
@@ -494,14 +490,21 @@ node_gemm_kernel(TcGemmParams p) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_hi = tmem_d + a_col0 + static_cast<uint32_t>(stg * kAStageCols);
         const uint32_t a_lo = a_hi + 32u;
-        const uint64_t w_hi = dw_hi0 + static_cast<uint64_t>(static_cast<uint32_t>(kc) * w_panel16);
-        const uint64_t w_lo = dw_lo0 + static_cast<uint64_t>(static_cast<uint32_t>(kc) * w_panel16);
+        const uint64_t w_hi = dw0 + static_cast<uint64_t>(static_cast<uint32_t>(kc) * w_block16);
+        const uint64_t w_lo = w_hi + w_lo16;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {  // a k-step is 8 TMEM columns of A and 32 bytes = 2 descriptor units of W
           if (jj < ksteps) {
-            umma_tf32_ts_pred(d_addr, a_hi + 8 * jj, w_hi + 2 * jj, idesc, (kc > 0 || jj > 0) ? 1u : 0u, leader);
-            umma_tf32_ts_pred(d_addr, a_lo + 8 * jj, w_hi + 2 * jj, idesc, 1u, leader);
-            umma_tf32_ts_pred(d_addr, a_hi + 8 * jj, w_lo + 2 * jj, idesc, 1u, leader);
+            const uint32_t acc = (kc > 0 || jj > 0) ? 1u : 0u;
+            if (dual) {
+              // D[:, 0:np] += A_hi W_hi^T, D[:, np:2np] += A_hi W_lo^T in one instruction, then D[:, 0:np] += A_lo W_hi^T
+              umma_tf32_ts_pred(d_addr, a_hi + 8 * jj, w_hi + 2 * jj, idesc2, acc, leader);
+              umma_tf32_ts_pred(d_addr, a_lo + 8 * jj, w_hi + 2 * jj, idesc, 1u, leader);
+            } else {
+              umma_tf32_ts_pred(d_addr, a_hi + 8 * jj, w_hi + 2 * jj, idesc, acc, leader);
+              umma_tf32_ts_pred(d_addr, a_lo + 8 * jj, w_hi + 2 * jj, idesc, 1u, leader);
+              umma_tf32_ts_pred(d_addr, a_hi + 8 * jj, w_lo + 2 * jj, idesc, 1u, leader);
+            }
           }
         }
         umma_commit_pred(&a_empty[stg], leader);   // arrives when the MMAs above have finished reading the stage
@@ -512,6 +515,26 @@ node_gemm_kernel(TcGemmParams p) {
     }
   } else {
     // =========================== epilogue ===========================
+    // one-time setup, part 2 (overlaps the first tile's loads): resident weights, bias, BatchNorm-on-load
+    // parameters -> shared memory, published through setup_bar
+    {
+      const int et0 = tid - kProducerThreads;
+      const int total16 = (2 * np * kp32) >> 2;
+      const uint32_t w_addr = smem_u32(s.w);
+      for (int i = et0; i < total16; i += kEpilogueThreads) cp_async16(w_addr + i * 16u, p.wpack + i * 4, 16);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      for (int i = et0; i < np; i += kEpilogueThreads) s.bias[i] = (p.bias != nullptr && i < p.n) ? p.bias[i] : 0.f;
+      if (p.a1_mean != nullptr) {
+        const int k1r = (p.k1 + 3) & ~3;
+        for (int i = et0; i < p.k1; i += kEpilogueThreads) {
+          s.bn[i] = p.a1_mean[i]; s.bn[k1r + i] = p.a1_scale[i]; s.bn[2 * k1r + i] = p.a1_beta[i];
+        }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // W: generic-proxy writes -> async proxy (MMA)
+      mbar_arrive(setup_bar);
+      if (!mbar_wait(setup_bar, 0u)) timed_out = true;
+    }
     // thread = row (TMEM lane), 16 columns per tcgen05.ld; each lane stores 4 x 16 bytes of its own
     // row; BatchNorm column sums via a fixed-order butterfly over the warp's 32 rows.
     const int ew = warp - kProducerWarps;      // 0..7
@@ -547,17 +570,29 @@ node_gemm_kernel(TcGemmParams p) {
         const int rows_valid = static_cast<int>(p.m - tile_row0 < 32 ? p.m - tile_row0 : 32);
         const int c4 = lane & 7, rsub = lane >> 3;
         for (int cd = half; cd < n_dbl; cd += 2) {
-          const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ab * np + cd * 32);
+          const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ab * acc_stride + cd * 32);
           float* strow = st + lane * 36;
           if (cd * 2 + 1 < n_blocks) {
             uint32_t r[32];
             tmem_ld32(taddr, r);
+            if (dual) {   // second half of the accumulator: the hi * lo products
+              uint32_t r2[32];
+              tmem_ld32(taddr + np, r2);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            }
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4)
               *reinterpret_cast<uint4*>(strow + j4 * 4) = make_uint4(r[j4 * 4], r[j4 * 4 + 1], r[j4 * 4 + 2], r[j4 * 4 + 3]);
           } else {
             uint32_t r[16];
             tmem_ld16(taddr, r);
+            if (dual) {
+              uint32_t r2[16];
+              tmem_ld16(taddr + np, r2);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            }
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4)
               *reinterpret_cast<uint4*>(strow + j4 * 4) = make_uint4(r[j4 * 4], r[j4 * 4 + 1], r[j4 * 4 + 2], r[j4 * 4 + 3]);
@@ -586,7 +621,13 @@ node_gemm_kernel(TcGemmParams p) {
       } else
       for (int cb = half; cb < n_blocks; cb += 2) {
         uint32_t r[16];
-        tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ab * np + cb * 16), r);
+        tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ab * acc_stride + cb * 16), r);
+        if (dual) {   // second half of the accumulator: the hi * lo products
+          uint32_t r2[16];
+          tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ab * acc_stride + np + cb * 16), r2);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
         float v[16];
         const bool full_block = cb * 16 + 16 <= p.n;   // no padding columns inside this block
 #pragma unroll
@@ -690,9 +731,12 @@ size_t smem_bytes_for(int np, int kp, int raw_slots, int staged = 0) {
                           2 * kBarCount + 4 + (staged ? kStageFloats : 0)) + kMaxPanels * sizeof(PanelInfo) + 64;
 }
 
-// TMEM: two accumulators of np columns + A stages of 64 columns each
+// hi*hi and hi*lo in one MMA (N = 2 np <= 256) when TMEM still holds two such accumulators + 2 A stages
+bool pick_dual(int np) { return 2 * np <= 256 && 4 * np + 2 * kAStageCols <= 512; }
+
+// TMEM: two accumulators of np (dual: 2 np) columns + A stages of 64 columns each
 int pick_a_stages(int np) {
-  const int st = (512 - 2 * np) / kAStageCols;
+  const int st = (512 - (pick_dual(np) ? 4 : 2) * np) / kAStageCols;
   return st > kMaxAStages ? kMaxAStages : st;
 }
 
@@ -761,6 +805,7 @@ int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
   p.kp = tc_seg_pad(p.k1) + tc_seg_pad(p.k2) + tc_seg_pad(p.kt) + tc_seg_pad(p.k3);
   if (p.n_store < p.n) p.n_store = p.n;
   p.a_stages = pick_a_stages(p.np);
+  p.dual = pick_dual(p.np) ? 1 : 0;
   // coalesced (staged) epilogue when there is neither residual nor BatchNorm sums, the rows allow
   // 16-byte stores and the transpose buffers still leave room for the raw ring
   p.staged_epilogue = (p.residual == nullptr && p.bn_partial == nullptr && (p.ldy & 3) == 0 && (p.n_store & 3) == 0 &&

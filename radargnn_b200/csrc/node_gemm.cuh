@@ -41,7 +41,7 @@ struct TcGemmParams {
   const float* a1_mean = nullptr; const float* a1_scale = nullptr; const float* a1_beta = nullptr;
   int32_t relu_a1 = 0, relu_a2 = 0;
   const float* wpack = nullptr;                                  // tc_pack_weights image
-  int32_t n = 0, np = 0, kp = 0, a_stages = 0, raw_slots = 0, staged_epilogue = 0;
+  int32_t n = 0, np = 0, kp = 0, a_stages = 0, raw_slots = 0, staged_epilogue = 0, dual = 0;
   const float* bias = nullptr;
   const float* residual = nullptr; int64_t ldr = 0;
   const float* res_mean = nullptr; const float* res_scale = nullptr; const float* res_beta = nullptr;

@@ -21,7 +21,7 @@ for tag in (b"node_gemm_pre", b"node_gemm_post", b"node_gemm_pre@2", b"node_gemm
     torch.cuda.synchronize()
     t = buf.cpu().numpy().reshape(4, 32, 2)
     t0 = t[3, 0, 0]
-    print(tag.decode(), "kernel cycles (CTA 0):", t[3, 0, 1] - t0)
+    print(tag.decode(), "kernel cycles (CTA 0):", t[3, 0, 1] - t0, " setup part 1 cycles:", t0 - buf.cpu().numpy()[3 * 64 + 63])
     tag = tag.split(b"@")[0]
     for tl in range(8):
         if t[0, tl, 0] == 0: break
