@@ -16,6 +16,7 @@
 // Linear layers before the segmented reduce.  An edge encoder (Linear De -> C) is folded into
 // W_e and b.  Results differ from the reference only by fp32 rounding order.
 #include <math.h>
+#include <stdlib.h>
 
 #include "conv.cuh"
 
@@ -213,10 +214,12 @@ edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, 
 // and edge attributes are loaded once per 8 slots (lane = slot) and four slots = 16 gathers per lane are
 // in flight.  The edge term runs on packed FFMA2, max / min on the 3-input FMNMX3.  The p - 128 tail
 // channels live in their own narrow arrays and are processed slot-parallel (lane = slot) with a fixed
-// butterfly over the 8 lanes at the end of the row.  A CTA covers kSplitRows consecutive (cell-sorted)
-// nodes, 16 at a time, so that concurrently gathered sources overlap in L1.
-constexpr int kSplitRows = 64;
-constexpr int kSplitThreads = 128;
+// butterfly over the 8 lanes at the end of the row.  One persistent CTA per SM walks a CONTIGUOUS range of
+// (cell-sorted) nodes, 48 at a time: everything an SM gathers concurrently, and from one pass to the
+// next, comes from the same few grid rows, so the L1 working set stays small (more, independent CTAs per
+// SM measured slower: 3 -> 4 -> 5 resident 64-row blocks took 95 -> 116 -> 217 us, L1 thrashing).
+constexpr int kSplitThreads = 384;                      // 12 warps: one persistent CTA per SM (168 registers per thread)
+constexpr int kSplitPassRows = kSplitThreads / 32 * 4;  // rows a CTA works on at a time
 constexpr int kSplitMain = 128;
 
 __device__ __forceinline__ float4 fma4x2(float s, float4 w, float4 a) {
@@ -243,12 +246,12 @@ __device__ __forceinline__ float4 combine4x2(float4 a, float4 v0, float4 v1) {
 }
 
 template <int MODE, int DE>
-__global__ void __launch_bounds__(kSplitThreads, 3)
+__global__ void __launch_bounds__(kSplitThreads, 1)
 edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restrict__ bt, int p,
                             const float* __restrict__ bias, const float* __restrict__ w_e, int64_t ldwe,
                             const float* __restrict__ ea, const int32_t* __restrict__ csc_ptr,
-                            const int32_t* __restrict__ csc_src, int n_nodes, float* __restrict__ out_m,
-                            float* __restrict__ out_t, IsolatedNodeTerm iso) {
+                            const int32_t* __restrict__ csc_src, int n_nodes, int rows_per_cta,
+                            float* __restrict__ out_m, float* __restrict__ out_t, IsolatedNodeTerm iso) {
   constexpr int kW = kSplitMain + 4;             // staged channels: main + one float4 of tail
   __shared__ __align__(16) float ws[DE][kW];     // W_e transposed: ws[d][channel], zero beyond p
   __shared__ __align__(16) float bs[kW];         // message bias, zero beyond p
@@ -270,19 +273,21 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
   constexpr float kInit = MODE == RGNN_AGGR_MAX ? -INFINITY : (MODE == RGNN_AGGR_MIN ? INFINITY : 0.f);
   const float4 init4 = make_float4(kInit, kInit, kInit, kInit);
   const float* bcol = bm + 4 * q;
-  constexpr int kPasses = kSplitRows / 16;
+  const int row_begin = blockIdx.x * rows_per_cta;
+  const int row_end = min(n_nodes, row_begin + rows_per_cta);
+  const int kPasses = (max(row_end - row_begin, 0) + kSplitPassRows - 1) / kSplitPassRows;
   constexpr bool kOrderFree = MODE == RGNN_AGGR_MAX || MODE == RGNN_AGGR_MIN;
   constexpr int kHold = 4;                       // slots held per lane: a quarter holds 8 * kHold = 32 slots of its row
-  const int row_base = blockIdx.x * kSplitRows + warp * 4 + quarter;
+  const int row_base = row_begin + warp * 4 + quarter;
 
   // Software pipeline over the passes: the row pointers run two passes ahead and the first 32 slots
   // (lane q holds slots q, q + 8, q + 16, q + 24: source index, edge attributes) one pass ahead, so that
   // a pass starts its gathers without waiting for an index load.
   struct SlotRegs { int src[kHold]; float e[kHold][DE]; };
   auto load_ptr = [&](int pass, int& beg, int& deg) {
-    const int row = row_base + pass * 16;
+    const int row = row_base + pass * kSplitPassRows;
     beg = 0; deg = 0;
-    if (pass < kPasses && row < n_nodes) { beg = csc_ptr[row]; deg = csc_ptr[row + 1] - beg; }
+    if (pass < kPasses && row < row_end) { beg = csc_ptr[row]; deg = csc_ptr[row + 1] - beg; }
   };
   auto load_slots = [&](int beg, int deg, int b, SlotRegs& r) {
 #pragma unroll
@@ -306,8 +311,8 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
   load_slots(beg, deg, 0, pre);
 
   for (int it = 0; it < kPasses; ++it) {
-    const int row = row_base + it * 16;
-    const bool live = row < n_nodes;
+    const int row = row_base + it * kSplitPassRows;
+    const bool live = row < row_end;
     load_ptr(it + 2, beg2, deg2);
     SlotRegs cur = pre;
     load_slots(beg1, deg1, 0, pre);   // next pass (zeros past the last pass)
@@ -457,12 +462,16 @@ int launch_edge_aggregate_split_mode(const float* bm, const float* bt, const Con
                                      const float* w_e, int64_t ldwe, const float* ea, const int32_t* csc_ptr,
                                      const int32_t* csc_src, int64_t n_nodes, float* out_m, float* out_t,
                                      cudaStream_t stream, const IsolatedNodeTerm& iso) {
-  const unsigned blocks = div_up(n_nodes, kSplitRows);
+  // one persistent CTA per SM over a contiguous node range (a multiple of the pass size)
   const int n = static_cast<int>(n_nodes);
+  const int ctas = sm_count();
+  int rows_per_cta = static_cast<int>((n_nodes + ctas - 1) / ctas);
+  rows_per_cta = (rows_per_cta + kSplitPassRows - 1) / kSplitPassRows * kSplitPassRows;
+  const unsigned blocks = div_up(n_nodes, rows_per_cta);
 #define RGNN_SPLIT_CASE(DE_)                                                                                   \
   case DE_:                                                                                                    \
     edge_aggregate_split_kernel<MODE, DE_><<<blocks, kSplitThreads, 0, stream>>>(bm, bt, s.p, bias, w_e, ldwe, ea, csc_ptr, \
-                                                                        csc_src, n, out_m, out_t, iso);       \
+                                                                                 csc_src, n, rows_per_cta, out_m, out_t, iso); \
     break;
   switch (s.de) {
     RGNN_SPLIT_CASE(1) RGNN_SPLIT_CASE(2) RGNN_SPLIT_CASE(3) RGNN_SPLIT_CASE(4)

@@ -165,21 +165,24 @@ fold_weights_kernel(const float* __restrict__ w_m, int64_t ld_m, const float* __
 // Shared memory then only holds W (resident) and the raw ring; there is no swizzled A stage, no
 // generic->async proxy fence, and TMEM (512 columns) has room for the two accumulators plus 3-4 A stages.
 //
-// Warp roles (672 threads, one CTA per SM, persistent over 128-row tiles):
-//   warps 0-3   loaders: cp.async 16-byte items of a panel into the ring slot (8 lanes per 128-byte row
+// Warp roles (736 threads, one CTA per SM, persistent over 128-row tiles; a warp may only touch the TMEM
+// lane quarter warp_id % 4, so every group of four consecutive warps covers all 128 lanes):
+//   warps 0-1   loaders: cp.async 16-byte items of a panel into the ring slot (8 lanes per 128-byte row
 //               segment, zero fill for rows / columns beyond the operand), completion via
 //               cp.async.mbarrier.arrive on raw_full[slot]
-//   warps 4-11  converters, two groups of four (one warp per TMEM lane quarter) alternating panels:
+//   warps 2-13  converters, three groups of four taking panels round-robin (the per-panel chain wait ->
+//               LDS -> split -> tcgen05.st -> wait::st -> arrive is latency-bound, so panels overlap):
 //               thread = row, 32 floats from the ring (swizzled: conflict-free), transform, split,
 //               2 x 2 tcgen05.st.x16 -> a_full[stage]; the slot goes back to the loaders (raw_empty)
-//   warps 12-19 epilogue: TMEM -> registers -> global (+ BatchNorm column sums); two warps per TMEM lane
-//               quarter, alternating 16-column blocks
-//   warp  20    MMA issuer (one lane): per k-step hi*hi + lo*hi + hi*lo, tcgen05.commit -> a_empty / acc_full
+//   warps 14-21 epilogue: TMEM -> registers -> transpose buffer -> coalesced global stores (+ residual,
+//               BatchNorm column sums); two warps per TMEM lane quarter, alternating 32-column blocks
+//   warp  22    MMA issuer (one lane): per k-step hi*hi + lo*hi + hi*lo, tcgen05.commit -> a_empty / acc_full
 constexpr int kMaxRaw = 6;
 constexpr int kMaxAStages = 4;
-constexpr int kLoaderWarps = 4, kConvWarps = 8;
+constexpr int kLoaderWarps = 2, kConvGroups = 3, kConvWarps = 4 * kConvGroups;
 constexpr int kLoaderThreads = kLoaderWarps * 32;
-constexpr int kConvGroupThreads = 128;            // one converter group = 4 warps
+constexpr int kLoaderItems = 1024 / kLoaderThreads;   // 16-byte items of a panel per loader thread
+constexpr int kConvGroupThreads = 128;            // one converter group = 4 warps, one per TMEM lane quarter
 constexpr int kEpilogueThreads = 256;
 constexpr int kEpiWarp0 = kLoaderWarps + kConvWarps;
 constexpr int kProducerWarps = kEpiWarp0;         // warps in front of the epilogue warps
@@ -343,23 +346,20 @@ node_gemm_kernel(TcGemmParams p) {
 
   if (warp < kLoaderWarps) {
     // =========================== loaders ===========================
-    // warp w streams rows 32 w .. 32 w + 31 of every panel: item i of a lane = row 32 w + 4 i + lane / 8,
+    // warp w streams rows 64 w .. 64 w + 63 of every panel: item i of a lane = row 64 w + 4 i + lane / 8,
     // 16-byte chunk lane % 8 (a warp instruction covers four whole 128-byte row segments)
     const int c = lane & 7;
-    const int rsub = warp * 32 + (lane >> 3);
+    const int rsub = warp * (kRows / kLoaderWarps) + (lane >> 3);
     const uint32_t raw_addr = smem_u32(s.raw);
     int tl = 0, pi = 0, slot = 0;
     uint32_t wrap = 0;   // how often the ring has wrapped
-    int64_t rr[8];       // source rows of this thread's items (through the optional gather map), per tile
-    bool rok[8];
+    int32_t rr[kLoaderItems];   // source rows of this thread's items (through the optional gather map), per tile; -1: none
     auto tile_rows = [&](int t) {
       const int row0 = static_cast<int>(blockIdx.x + static_cast<int64_t>(t) * gridDim.x) * kRows;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kLoaderItems; ++i) {
         const int row = row0 + rsub + 4 * i;
-        rok[i] = row < m32;
-        const int rc = rok[i] ? row : 0;
-        rr[i] = p.a1_rows != nullptr ? static_cast<int64_t>(p.a1_rows[rc]) : static_cast<int64_t>(rc);
+        rr[i] = row < m32 ? (p.a1_rows != nullptr ? p.a1_rows[row] : row) : -1;
       }
     };
     if (total > 0) tile_rows(0);
@@ -374,10 +374,10 @@ node_gemm_kernel(TcGemmParams p) {
       const int64_t ld = info.ld;
       const uint32_t slot_addr = raw_addr + static_cast<uint32_t>(slot) * (kABufFloats * 4u);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kLoaderItems; ++i) {
         const int rl = rsub + 4 * i;
-        const bool ok = col_ok && rok[i];
-        const int64_t r = gather ? rr[i] : static_cast<int64_t>(row0 + rl);
+        const bool ok = col_ok && rr[i] >= 0;
+        const int64_t r = gather ? static_cast<int64_t>(rr[i]) : static_cast<int64_t>(row0 + rl);
         const float* src = ok ? colp + r * ld : p.a1;
         cp_async16(slot_addr + static_cast<uint32_t>(rl * 32 + ((c ^ (rl & 7)) << 2)) * 4u, src, ok ? 16u : 0u);
       }
@@ -392,77 +392,92 @@ node_gemm_kernel(TcGemmParams p) {
     asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp < kEpiWarp0) {
     // =========================== converters ===========================
-    const int grp = (warp - kLoaderWarps) >> 2;       // group 0: even panels, group 1: odd panels
+    const int grp = (warp - kLoaderWarps) >> 2;       // group g takes panels g, g + 3, g + 6, ...
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
     const int rl = quarter * 32 + lane;               // row of the tile = TMEM lane
     const uint32_t lane_addr = tmem_d + (static_cast<uint32_t>(quarter * 32) << 16) + a_col0;
     const int k1r = (p.k1 + 3) & ~3;
     const float* rawrow = s.raw + rl * 32;
     const int sw = rl & 7;
+    const bool tracer = trace != nullptr && tid == kLoaderThreads;
+    // A waiter may be at most one barrier phase ahead of the phase in flight (the parity test cannot tell
+    // two phases apart), so no more groups take panels than there are ring slots and TMEM stages.
+    const int n_groups = min(kConvGroups, min(raw_slots, a_stages));
     if (!mbar_wait(setup_bar, 0u)) timed_out = true;   // BatchNorm-on-load parameters are in shared memory
-    // (tile, panel), ring slot and TMEM stage of panel g, advanced by two panels per iteration
+    // (tile, panel), ring slot and TMEM stage of panel g, advanced by kConvGroups panels per iteration
     int tl = 0, pi = grp, slot = grp, stg = grp;
     uint32_t raw_round = 0, a_round = 0;
     while (pi >= panels) { pi -= panels; ++tl; }
+    while (slot >= raw_slots) { slot -= raw_slots; ++raw_round; }
     while (stg >= a_stages) { stg -= a_stages; ++a_round; }
-    for (int g = grp; g < total; g += 2) {
+    for (int g = grp; g < total && grp < n_groups; g += n_groups) {
       const PanelInfo& info = s.panel[pi];
-      const int flags = info.flags;
-      const int row = static_cast<int>(blockIdx.x + static_cast<int64_t>(tl) * gridDim.x) * kRows + rl;
-      const bool row_ok = row < m32;
-      float rs = 1.f;
-      if ((flags & kPanelRowScale) && row_ok) {
-        const int deg = p.csc_ptr[row + 1] - p.csc_ptr[row];
-        rs = p.rowscale_mode == 2 ? static_cast<float>(deg) : (deg > 0 ? 1.f : 0.f);
-      }
-      if (trace != nullptr && tid == kLoaderThreads && g < 30) trace[3 * 64 + 2 + (g >> 1) * 4] = clock64();
+      const int flags = info.flags & (kPanelBn | kPanelRelu | kPanelRowScale);
+      if (tracer && g < 45) trace[3 * 64 + 2 + (g / 3) * 4] = clock64();
       if (!mbar_wait(&raw_full[slot], raw_round & 1u)) timed_out = true;
-      if (trace != nullptr && tid == kLoaderThreads && g < 30) trace[3 * 64 + 3 + (g >> 1) * 4] = clock64();
+      if (tracer && g < 45) trace[3 * 64 + 3 + (g / 3) * 4] = clock64();
       const float* src = rawrow + static_cast<size_t>(slot) * kABufFloats;
       float4 v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(src + ((j ^ sw) << 2));
-      // the MMAs of the previous use of this TMEM stage must have drained it
-      bool waited = false;
+      if (flags != 0) {
+        // transform in place: BatchNorm + ReLU of the previous layer on load, row scale.  Rows and columns
+        // beyond the operand were zero-filled by the loaders and must stay zero after the affine map.
+        const int row = static_cast<int>(blockIdx.x + static_cast<int64_t>(tl) * gridDim.x) * kRows + rl;
+        const bool row_ok = row < m32;
+        float rs = 1.f;
+        if ((flags & kPanelRowScale) && row_ok) {
+          const int deg = p.csc_ptr[row + 1] - p.csc_ptr[row];
+          rs = p.rowscale_mode == 2 ? static_cast<float>(deg) : (deg > 0 ? 1.f : 0.f);
+        }
+        if (!row_ok) rs = 0.f;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float hi[16], lo[16];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = h * 4 + jj;
+        for (int j = 0; j < 8; ++j) {
           float4 x = v[j];
           const int colc = info.col0 + 4 * j;
-          if (flags & kPanelBn) {
-            const bool cv = 4 * j < info.valid;
-            const float4 mu = cv ? *reinterpret_cast<const float4*>(s.bn + colc) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 sc = cv ? *reinterpret_cast<const float4*>(s.bn + k1r + colc) : mu;
-            const float4 be = cv ? *reinterpret_cast<const float4*>(s.bn + 2 * k1r + colc) : mu;
+          const bool cv = 4 * j < info.valid;
+          if ((flags & kPanelBn) && cv) {
+            const float4 mu = *reinterpret_cast<const float4*>(s.bn + colc);
+            const float4 sc = *reinterpret_cast<const float4*>(s.bn + k1r + colc);
+            const float4 be = *reinterpret_cast<const float4*>(s.bn + 2 * k1r + colc);
             x.x = (x.x - mu.x) * sc.x + be.x; x.y = (x.y - mu.y) * sc.y + be.y;
             x.z = (x.z - mu.z) * sc.z + be.z; x.w = (x.w - mu.w) * sc.w + be.w;
           }
           if (flags & kPanelRelu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-          if (flags & kPanelRowScale) { x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs; }
-          if (!row_ok) x = make_float4(0.f, 0.f, 0.f, 0.f);   // zero-filled rows must stay zero after the affine transform
-          split_tf32(x.x, hi[jj * 4 + 0], lo[jj * 4 + 0]); split_tf32(x.y, hi[jj * 4 + 1], lo[jj * 4 + 1]);
-          split_tf32(x.z, hi[jj * 4 + 2], lo[jj * 4 + 2]); split_tf32(x.w, hi[jj * 4 + 3], lo[jj * 4 + 3]);
+          x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
+          v[j] = x;
         }
-        if (!waited) {
-          if (a_round >= 1u && !mbar_wait(&a_empty[stg], (a_round - 1u) & 1u)) timed_out = true;
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          waited = true;
-        }
+      }
+      // the MMAs of the previous use of this TMEM stage must have drained it
+      if (a_round >= 1u && !mbar_wait(&a_empty[stg], (a_round - 1u) & 1u)) timed_out = true;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float t[16];
         const uint32_t col = static_cast<uint32_t>(stg * kAStageCols + h * 16);
-        tmem_st16(lane_addr + col, hi);
-        tmem_st16(lane_addr + col + 32, lo);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {   // hi parts
+          const float4 x = v[h * 4 + jj];
+          t[jj * 4 + 0] = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); t[jj * 4 + 1] = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          t[jj * 4 + 2] = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); t[jj * 4 + 3] = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+        }
+        tmem_st16(lane_addr + col, t);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {   // lo parts = x - hi (exact)
+          const float4 x = v[h * 4 + jj];
+          t[jj * 4 + 0] = x.x - t[jj * 4 + 0]; t[jj * 4 + 1] = x.y - t[jj * 4 + 1];
+          t[jj * 4 + 2] = x.z - t[jj * 4 + 2]; t[jj * 4 + 3] = x.w - t[jj * 4 + 3];
+        }
+        tmem_st16(lane_addr + col + 32, t);
       }
       mbar_arrive(&raw_empty[slot]);   // the panel is in registers / TMEM: the slot can be refilled
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&a_full[stg]);
-      if (trace != nullptr && tid == kLoaderThreads && g < 30) trace[3 * 64 + 4 + (g >> 1) * 4] = clock64();
-      pi += 2; while (pi >= panels) { pi -= panels; ++tl; }
-      slot += 2; if (slot >= raw_slots) { slot -= raw_slots; ++raw_round; }
-      stg += 2; while (stg >= a_stages) { stg -= a_stages; ++a_round; }
+      if (tracer && g < 45) trace[3 * 64 + 4 + (g / 3) * 4] = clock64();
+      pi += n_groups; while (pi >= panels) { pi -= panels; ++tl; }
+      slot += n_groups; while (slot >= raw_slots) { slot -= raw_slots; ++raw_round; }
+      stg += n_groups; while (stg >= a_stages) { stg -= a_stages; ++a_round; }
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
@@ -538,7 +553,7 @@ node_gemm_kernel(TcGemmParams p) {
     // thread = row (TMEM lane), 16 columns per tcgen05.ld; each lane stores 4 x 16 bytes of its own
     // row; BatchNorm column sums via a fixed-order butterfly over the warp's 32 rows.
     const int ew = warp - kProducerWarps;      // 0..7
-    const int q = ew & 3, half = ew >> 2;      // TMEM lane quarter, parity of the column blocks
+    const int q = warp & 3, half = ew >> 2;    // TMEM lane quarter (hardware: warp id % 4), parity of the column blocks
     const int n_blocks = np >> 4;
     const bool vec = ((p.ldy & 3) == 0) && ((p.n_store & 3) == 0);
     const int et = tid - kProducerThreads;     // 0..255
@@ -599,6 +614,7 @@ node_gemm_kernel(TcGemmParams p) {
           }
           __syncwarp();
           const int col = cd * 32 + c4 * 4;
+          float4 csum4 = make_float4(0.f, 0.f, 0.f, 0.f), csq4 = csum4;
           if (col < p.n_store && col < np) {
             const float4 bv = *reinterpret_cast<const float4*>(s.bias + col);
             // split output: columns from n_split on go to the narrow tail array y2
@@ -607,13 +623,60 @@ node_gemm_kernel(TcGemmParams p) {
             if (col < n_split) { ld = p.ldy; dst = p.y + (tile_row0 + rsub) * ld + col; }
             else { ld = p.ldy2; dst = p.y2 + (tile_row0 + rsub) * ld + (col - n_split); }
             const float* srow = st + rsub * 36 + c4 * 4;
+            // residual (RadarPointGNNConv): the layer input, normalised on load like the A operand
+            const bool has_res = p.residual != nullptr && col < p.n;
+            float4 rmu = make_float4(0.f, 0.f, 0.f, 0.f), rsc = make_float4(1.f, 1.f, 1.f, 1.f), rbe = rmu;
+            if (has_res && p.res_mean != nullptr) {
+              rmu = *reinterpret_cast<const float4*>(p.res_mean + col);
+              rsc = *reinterpret_cast<const float4*>(p.res_scale + col);
+              rbe = *reinterpret_cast<const float4*>(p.res_beta + col);
+            }
+            if (!has_res && p.bn_partial == nullptr) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                if (it * 4 + rsub < rows_valid) {
+                  float4 v4 = *reinterpret_cast<const float4*>(srow + it * (4 * 36));
+                  v4.x += bv.x; v4.y += bv.y; v4.z += bv.z; v4.w += bv.w;
+                  *reinterpret_cast<float4*>(dst + it * 4 * ld) = v4;
+                }
+              }
+            } else
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               if (it * 4 + rsub < rows_valid) {
                 float4 v4 = *reinterpret_cast<const float4*>(srow + it * (4 * 36));
                 v4.x += bv.x; v4.y += bv.y; v4.z += bv.z; v4.w += bv.w;
+                if (has_res) {
+                  const int64_t grow = tile_row0 + rsub + it * 4;
+                  const int64_t rrow_i = p.a1_rows != nullptr ? static_cast<int64_t>(p.a1_rows[grow]) : grow;
+                  float4 rv = *reinterpret_cast<const float4*>(p.residual + rrow_i * p.ldr + col);
+                  if (p.res_mean != nullptr) {
+                    rv.x = (rv.x - rmu.x) * rsc.x + rbe.x; rv.y = (rv.y - rmu.y) * rsc.y + rbe.y;
+                    rv.z = (rv.z - rmu.z) * rsc.z + rbe.z; rv.w = (rv.w - rmu.w) * rsc.w + rbe.w;
+                  }
+                  if (p.res_relu) { rv.x = fmaxf(rv.x, 0.f); rv.y = fmaxf(rv.y, 0.f); rv.z = fmaxf(rv.z, 0.f); rv.w = fmaxf(rv.w, 0.f); }
+                  v4.x += rv.x; v4.y += rv.y; v4.z += rv.z; v4.w += rv.w;
+                }
                 *reinterpret_cast<float4*>(dst + it * 4 * ld) = v4;
+                csum4.x += v4.x; csum4.y += v4.y; csum4.z += v4.z; csum4.w += v4.w;
+                csq4.x = fmaf(v4.x, v4.x, csq4.x); csq4.y = fmaf(v4.y, v4.y, csq4.y);
+                csq4.z = fmaf(v4.z, v4.z, csq4.z); csq4.w = fmaf(v4.w, v4.w, csq4.w);
               }
+            }
+          }
+          if (p.bn_partial != nullptr) {
+            // column sums of the warp's 32 rows: the four row groups (lanes c4, c4 + 8, + 16, + 24) in a
+            // fixed order -> deterministic
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              csum4.x += __shfl_xor_sync(0xffffffffu, csum4.x, o); csum4.y += __shfl_xor_sync(0xffffffffu, csum4.y, o);
+              csum4.z += __shfl_xor_sync(0xffffffffu, csum4.z, o); csum4.w += __shfl_xor_sync(0xffffffffu, csum4.w, o);
+              csq4.x += __shfl_xor_sync(0xffffffffu, csq4.x, o); csq4.y += __shfl_xor_sync(0xffffffffu, csq4.y, o);
+              csq4.z += __shfl_xor_sync(0xffffffffu, csq4.z, o); csq4.w += __shfl_xor_sync(0xffffffffu, csq4.w, o);
+            }
+            if (rsub == 0 && col < np) {
+              *reinterpret_cast<float4*>(csum + col) = csum4;
+              *reinterpret_cast<float4*>(csq + col) = csq4;
             }
           }
           __syncwarp();
@@ -806,9 +869,14 @@ int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
   if (p.n_store < p.n) p.n_store = p.n;
   p.a_stages = pick_a_stages(p.np);
   p.dual = pick_dual(p.np) ? 1 : 0;
-  // coalesced (staged) epilogue when there is neither residual nor BatchNorm sums, the rows allow
-  // 16-byte stores and the transpose buffers still leave room for the raw ring
-  p.staged_epilogue = (p.residual == nullptr && p.bn_partial == nullptr && (p.ldy & 3) == 0 && (p.n_store & 3) == 0 &&
+  // coalesced (staged) epilogue whenever the rows allow 16-byte accesses and the transpose buffers still
+  // leave room for the raw ring
+  const bool res_ok = p.residual == nullptr ||
+                      ((p.ldr & 3) == 0 && (p.n & 3) == 0 && reinterpret_cast<uintptr_t>(p.residual) % 16 == 0 &&
+                       (p.res_mean == nullptr || (reinterpret_cast<uintptr_t>(p.res_mean) % 16 == 0 &&
+                                                  reinterpret_cast<uintptr_t>(p.res_scale) % 16 == 0 &&
+                                                  reinterpret_cast<uintptr_t>(p.res_beta) % 16 == 0)));
+  p.staged_epilogue = (res_ok && (p.ldy & 3) == 0 && (p.n_store & 3) == 0 && reinterpret_cast<uintptr_t>(p.y) % 16 == 0 &&
                        pick_raw_slots(p.np, p.kp, 1) >= 2) ? 1 : 0;
   p.raw_slots = pick_raw_slots(p.np, p.kp, p.staged_epilogue);
   if (p.raw_slots < 2 || p.a_stages < 1) return RGNN_ERR_UNSUPPORTED;
