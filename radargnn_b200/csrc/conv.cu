@@ -450,9 +450,11 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
       for (int i = 0; i < 4; ++i) r[i] = make_float4(-a16[i][0], -a16[i][1], -a16[i][2], -a16[i][3]);
       rt = make_float4(-t4[0], -t4[1], -t4[2], -t4[3]);
     }
-    float* orow = out_m + static_cast<int64_t>(row) * kSplitMain + 4 * q;
+    // M' is written panel-major (tc_panel_offset): panel i of the row's 128-row tile, row slot row % 128, the
+    // lane's 16-byte chunk at its swizzled position -- the eight lanes of the quarter fill one 128-byte line
+    float* orow = out_m + (static_cast<int64_t>(row >> 7) * (kSplitMain / 32)) * 4096 + (row & 127) * 32 + ((q ^ (row & 7)) << 2);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(orow + 32 * i) = r[i];
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(orow + i * 4096) = r[i];
     if (q == 0) *reinterpret_cast<float4*>(out_t + static_cast<int64_t>(row) * 4) = rt;
   }
 }
@@ -768,7 +770,7 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
     g2.a1 = in.x; g2.lda1 = in.ldx; g2.k1 = s.c; g2.a1_rows = in.rows;
     g2.a1_mean = in.mean; g2.a1_scale = in.scale; g2.a1_beta = in.beta; g2.relu_a1 = in.relu;
     g2.a2 = w.m; g2.lda2 = s.pp; g2.k2 = s.pp;
-    if (s.split) { g2.lda2 = s.pm; g2.k2 = s.pm; g2.at = w.mt; g2.ldat = s.pt4; g2.kt = s.pt4; }
+    if (s.split) { g2.lda2 = s.pm; g2.k2 = s.pm; g2.a2_panel_major = 1; g2.at = w.mt; g2.ldat = s.pt4; g2.kt = s.pt4; }
     if (third_segment) { g2.k3 = s.c; g2.csc_ptr = csc_ptr; g2.rowscale_mode = 2; }
     g2.wpack = wpack_post; g2.n = s.c_out; g2.n_store = s.c_out; g2.bias = d.post_bias[0];
     g2.y = first_out; g2.ldy = s.c_out; g2.m = n_nodes; g2.status = w.tc_status;

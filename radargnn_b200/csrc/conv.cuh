@@ -32,7 +32,7 @@ struct ConvShape {
 struct ConvWorkspace {
   float* a;        // [N, pp]  x W_t^T  (MPNN only)
   float* b;        // [N, pp]  x W_s^T            (split layout: [N, pm])
-  float* m;        // [N, pp]  aggregated messages (split layout: [N, pm])
+  float* m;        // [N, pp]  aggregated messages (split layout: pm / 32 swizzled panels per 128-row tile)
   float* bt;       // [N, pt4] tail channels of B  (split layout only)
   float* mt;       // [N, pt4] tail channels of M
   float* t1;       // [N, c_out] post_mlp ping-pong (post_layers > 1)
@@ -68,7 +68,8 @@ inline ConvWorkspace carve_conv_workspace(ArenaT& a, const rgnn_conv_desc& d, co
   const size_t npp = static_cast<size_t>(n_nodes) * (s.split ? s.pm : s.pp);
   w.a = (d.conv_type == RGNN_CONV_MPNN && !s.split) ? a.template take<float>(npp) : nullptr;  // unused on the tensor-core path
   w.b = a.template take<float>(npp);
-  w.m = a.template take<float>(npp);
+  // split layout: M' is panel-major (whole 128-row tiles), see node_gemm.cuh
+  w.m = a.template take<float>(s.split ? tc_panel_major_floats(n_nodes, s.pm) : npp);
   if (s.split) {
     w.bt = a.template take<float>(static_cast<size_t>(n_nodes) * s.pt4);
     w.mt = a.template take<float>(static_cast<size_t>(n_nodes) * s.pt4);

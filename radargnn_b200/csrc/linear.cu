@@ -164,6 +164,25 @@ bn_apply_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int c, cons
   y[(out_rows != nullptr ? out_rows[r] : r) * ldy + ch] = v;
 }
 
+// 16-byte variant: c % 4 == 0, rows and parameter arrays 16-byte aligned; c / 4 consecutive threads per row
+__global__ void __launch_bounds__(256)
+bn_apply_vec4_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int c4, const float* __restrict__ mean,
+                     const float* __restrict__ scale, const float* __restrict__ beta, int relu,
+                     float* __restrict__ y, int64_t ldy, const int32_t* __restrict__ out_rows) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n * c4) return;
+  const int64_t r = idx / c4;
+  const int ch = static_cast<int>(idx - r * c4) << 2;
+  const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + ch);
+  const float4 mu = *reinterpret_cast<const float4*>(mean + ch);
+  const float4 sc = *reinterpret_cast<const float4*>(scale + ch);
+  const float4 be = *reinterpret_cast<const float4*>(beta + ch);
+  float4 o = make_float4((v.x - mu.x) * sc.x + be.x, (v.y - mu.y) * sc.y + be.y, (v.z - mu.z) * sc.z + be.z,
+                         (v.w - mu.w) * sc.w + be.w);
+  if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+  *reinterpret_cast<float4*>(y + (out_rows != nullptr ? static_cast<int64_t>(out_rows[r]) : r) * ldy + ch) = o;
+}
+
 constexpr int kSumBlocks = 592;  // 4 x 148 SMs
 
 __global__ void __launch_bounds__(256)
@@ -189,12 +208,13 @@ sum_partial_kernel(const float* __restrict__ x, int64_t count, double* __restric
   }
 }
 
-__global__ void sum_final_kernel(const double* __restrict__ partial, int n, double* __restrict__ result) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < n; ++i) t += partial[i];
-    *result = t;
-  }
+// one warp: lane l adds partials l, l + 32, ... in order, then a fixed butterfly => deterministic
+__global__ void __launch_bounds__(32)
+sum_final_kernel(const double* __restrict__ partial, int n, double* __restrict__ result) {
+  double t = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) t += partial[i];
+  t = warp_sum(t);
+  if (threadIdx.x == 0) *result = t;
 }
 
 }  // namespace
@@ -243,7 +263,11 @@ int bn_apply(const float* x, int64_t ldx, int64_t n, int32_t c, const float* mea
              const float* beta, int32_t relu, float* y, int64_t ldy, cudaStream_t stream, const int32_t* out_rows) {
   if (n <= 0 || c <= 0) return RGNN_OK;
   RGNN_PROFILE("bn_apply", stream);
-  bn_apply_kernel<<<div_up(n * c, 256), 256, 0, stream>>>(x, ldx, n, c, mean, scale, beta, relu, y, ldy, out_rows);
+  auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  if (c % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && al16(x) && al16(y) && al16(mean) && al16(scale) && al16(beta))
+    bn_apply_vec4_kernel<<<div_up(n * (c / 4), 256), 256, 0, stream>>>(x, ldx, n, c / 4, mean, scale, beta, relu, y, ldy, out_rows);
+  else
+    bn_apply_kernel<<<div_up(n * c, 256), 256, 0, stream>>>(x, ldx, n, c, mean, scale, beta, relu, y, ldy, out_rows);
   RGNN_LAUNCH_CHECK();
   return RGNN_OK;
 }

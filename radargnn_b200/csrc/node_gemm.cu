@@ -192,7 +192,7 @@ constexpr int kGemmThreads = (kMmaWarp + 1) * 32;
 constexpr int kMaxPanels = 16;
 constexpr int kAStageCols = 64;                   // TMEM columns of one A stage: 32 hi + 32 lo
 
-enum PanelFlags : int32_t { kPanelBn = 1, kPanelRelu = 2, kPanelRowScale = 4, kPanelGather = 8 };
+enum PanelFlags : int32_t { kPanelBn = 1, kPanelRelu = 2, kPanelRowScale = 4, kPanelGather = 8, kPanelBulk = 16 };
 
 struct PanelInfo {
   const float* base;   // segment base pointer (column 0 of the segment)
@@ -319,6 +319,7 @@ node_gemm_kernel(TcGemmParams p) {
     } else if (k0 < k1p + k2p) {
       pi.base = p.a2; pi.ld = p.lda2; pi.col0 = k0 - k1p; pi.valid = min(32, p.k2 - pi.col0);
       pi.flags = p.relu_a2 ? kPanelRelu : 0;
+      if (p.a2_panel_major) { pi.flags |= kPanelBulk; pi.ld = p.k2 >> 5; }   // ld = panels per tile
     } else if (k0 < k1p + k2p + ktp) {
       pi.base = p.at; pi.ld = p.ldat; pi.col0 = k0 - k1p - k2p; pi.valid = min(32, p.kt - pi.col0);
       pi.flags = p.relu_a2 ? kPanelRelu : 0;
@@ -373,6 +374,20 @@ node_gemm_kernel(TcGemmParams p) {
       const bool gather = (info.flags & kPanelGather) != 0;
       const int64_t ld = info.ld;
       const uint32_t slot_addr = raw_addr + static_cast<uint32_t>(slot) * (kABufFloats * 4u);
+      if (info.flags & kPanelBulk) {
+        // panel-major operand: the whole panel is one contiguous 16 KB block, already in the ring's
+        // swizzled layout -> a single bulk copy that completes on the barrier's transaction count
+        if (tid == 0) {
+          const int64_t tile = blockIdx.x + static_cast<int64_t>(tl) * gridDim.x;
+          const float* src = info.base + ((tile * ld + (info.col0 >> 5)) << 12);
+          const uint32_t bar = smem_u32(&raw_full[slot]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kABufFloats * 4u) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(slot_addr), "l"(src), "r"(kABufFloats * 4u), "r"(bar) : "memory");
+        } else {
+          mbar_arrive(&raw_full[slot]);
+        }
+      } else {
 #pragma unroll
       for (int i = 0; i < kLoaderItems; ++i) {
         const int rl = rsub + 4 * i;
@@ -382,6 +397,7 @@ node_gemm_kernel(TcGemmParams p) {
         cp_async16(slot_addr + static_cast<uint32_t>(rl * 32 + ((c ^ (rl & 7)) << 2)) * 4u, src, ok ? 16u : 0u);
       }
       cp_async_arrive(&raw_full[slot]);
+      }
       if (++slot == raw_slots) { slot = 0; ++wrap; }
       if (++pi == panels) {
         if (trace != nullptr && tid == 0 && tl < 32) trace[0 * 64 + tl * 2 + 1] = clock64();
@@ -401,8 +417,10 @@ node_gemm_kernel(TcGemmParams p) {
     const int sw = rl & 7;
     const bool tracer = trace != nullptr && tid == kLoaderThreads;
     // A waiter may be at most one barrier phase ahead of the phase in flight (the parity test cannot tell
-    // two phases apart), so no more groups take panels than there are ring slots and TMEM stages.
-    const int n_groups = min(kConvGroups, min(raw_slots, a_stages));
+    // two phases apart) and panels do not complete in issue order (bulk copies vs. cp.async), so the host
+    // makes the ring slot and TMEM stage counts multiples of the group count: a slot / stage is then always
+    // used by the same group, which only waits for phase r after having consumed phase r - 1.
+    const int n_groups = p.conv_groups;
     if (!mbar_wait(setup_bar, 0u)) timed_out = true;   // BatchNorm-on-load parameters are in shared memory
     // (tile, panel), ring slot and TMEM stage of panel g, advanced by kConvGroups panels per iteration
     int tl = 0, pi = grp, slot = grp, stg = grp;
@@ -869,6 +887,7 @@ int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
   if (p.n_store < p.n) p.n_store = p.n;
   p.a_stages = pick_a_stages(p.np);
   p.dual = pick_dual(p.np) ? 1 : 0;
+  if (p.a2_panel_major && ((p.k2 & 31) != 0 || reinterpret_cast<uintptr_t>(p.a2) % 16 != 0)) return RGNN_ERR_INVALID_ARGUMENT;
   // coalesced (staged) epilogue whenever the rows allow 16-byte accesses and the transpose buffers still
   // leave room for the raw ring
   const bool res_ok = p.residual == nullptr ||
@@ -880,6 +899,10 @@ int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
                        pick_raw_slots(p.np, p.kp, 1) >= 2) ? 1 : 0;
   p.raw_slots = pick_raw_slots(p.np, p.kp, p.staged_epilogue);
   if (p.raw_slots < 2 || p.a_stages < 1) return RGNN_ERR_UNSUPPORTED;
+  // converter groups: ring slots and TMEM stages in multiples of the group count (see the converter role)
+  p.conv_groups = (p.raw_slots >= 3 && p.a_stages >= 3) ? 3 : ((p.raw_slots >= 2 && p.a_stages >= 2) ? 2 : 1);
+  p.raw_slots = p.raw_slots / p.conv_groups * p.conv_groups;
+  p.a_stages = p.a_stages / p.conv_groups * p.conv_groups;
   if (p.y2 != nullptr && (!p.staged_epilogue || (p.n_split & 3) != 0 || (p.ldy2 & 3) != 0)) return RGNN_ERR_UNSUPPORTED;
   const size_t smem = smem_bytes_for(p.np, p.kp, p.raw_slots, p.staged_epilogue);
   static size_t configured = 0;

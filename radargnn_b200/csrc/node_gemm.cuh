@@ -35,13 +35,15 @@ struct TcGemmParams {
   const float* a1 = nullptr; int64_t lda1 = 0; int32_t k1 = 0;   // 16-byte aligned rows, k1 % 4 == 0
   const int32_t* a1_rows = nullptr;                              // optional gather map for a1 / residual rows
   const float* a2 = nullptr; int64_t lda2 = 0; int32_t k2 = 0;   // optional, k2 % 4 == 0
+  int32_t a2_panel_major = 0;   // a2 is stored tile by tile as k2 / 32 swizzled [128 x 32] panels (tc_panel_offset): one
+                                // contiguous 16 KB block per panel, fetched with a single bulk copy (k2 % 32 == 0)
   const float* at = nullptr; int64_t ldat = 0; int32_t kt = 0;   // optional narrow tail of a2 (kt % 4 == 0, kt <= ldat)
   int32_t k3 = 0;                                                // 0, or k1: last segment rowscale * a1
   const int32_t* csc_ptr = nullptr; int32_t rowscale_mode = 0;   // 1: in-degree > 0, 2: in-degree
   const float* a1_mean = nullptr; const float* a1_scale = nullptr; const float* a1_beta = nullptr;
   int32_t relu_a1 = 0, relu_a2 = 0;
   const float* wpack = nullptr;                                  // tc_pack_weights image
-  int32_t n = 0, np = 0, kp = 0, a_stages = 0, raw_slots = 0, staged_epilogue = 0, dual = 0;
+  int32_t n = 0, np = 0, kp = 0, a_stages = 0, raw_slots = 0, staged_epilogue = 0, dual = 0, conv_groups = 0;
   const float* bias = nullptr;
   const float* residual = nullptr; int64_t ldr = 0;
   const float* res_mean = nullptr; const float* res_scale = nullptr; const float* res_beta = nullptr;
@@ -53,6 +55,13 @@ struct TcGemmParams {
   int32_t* status = nullptr;                                     // device flag set if a barrier wait timed out
   long long* trace = nullptr;                                    // debug timeline of CTA 0 (node_gemm.cu)
 };
+
+// float offset of element (row, col) of a panel-major operand with `panels` 32-float panels per 128-row tile
+__host__ __device__ inline int64_t tc_panel_offset(int64_t row, int col, int panels) {
+  const int rl = static_cast<int>(row & 127), c = (col & 31) >> 2;
+  return ((row >> 7) * panels + (col >> 5)) * 4096 + rl * 32 + ((c ^ (rl & 7)) << 2) + (col & 3);
+}
+inline size_t tc_panel_major_floats(int64_t rows, int k) { return static_cast<size_t>((rows + 127) / 128) * 128 * k; }
 
 bool tc_gemm_supported(const TcGemmShape& sh);
 size_t tc_pack_floats(const TcGemmShape& sh);
