@@ -316,10 +316,35 @@ def main_gpu(args, wl):
     for _ in range(max(3, args.warmup)):
         step_device()
     barrier()
+    count0 = _lib.launch_count()
+    step_device()
+    launches_per_step = _lib.launch_count() - count0   # kernels of librgnn_b200.so in one step
+    # The ~40 launches of a step are captured once into a CUDA graph and replayed: the first kernels of a
+    # step (14 short cell-list launches) are otherwise bound by host launch latency, not by the GPU.
+    step_eager = step_device
+    graph = None
+    if not args.no_graph:
+        def step_kernels():
+            _lib.check(lib.rgnn_pipeline_forward(C.byref(handle.desc), pos_d.data_ptr(), vel_d.data_ptr(), x0_d.data_ptr(),
+                                                 ptr.ctypes.data, n_frames, edge_index.data_ptr(), n_edges,
+                                                 edge_attr.data_ptr(), h.data_ptr(), flag.data_ptr(), ws.data_ptr(),
+                                                 ws.numel(), torch.cuda.current_stream().cuda_stream))
+            _lib.check(lib.rgnn_sum_f32(h.data_ptr(), h.numel(), loss.data_ptr(), sum_ws.data_ptr(), sum_ws.numel(),
+                                        torch.cuda.current_stream().cuda_stream))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step_kernels()
+
+        def step_device():
+            graph.replay()
+            if world > 1:
+                dist.all_reduce(loss[:1])
+        for _ in range(3):
+            step_device()
+        barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = _lib.launch_count()
     t_dev = timed(step_device, args.steps)
-    launches = _lib.launch_count() - launches0
+    launches = launches_per_step * args.steps   # a graph replay launches the same kernels as the captured eager step
     barrier()
     t_dev = max_over_ranks(t_dev)
     if int(flag.item()) != 0:
@@ -352,7 +377,7 @@ def main_gpu(args, wl):
     # ---- roofline of the dominant kernel: per-kernel CUDA events over the same steps ----------------
     _lib.profile_reset()
     _lib.profile_enable(True)
-    timed(step_device, args.steps)
+    timed(step_eager, args.steps)   # per-kernel events need eager launches
     _lib.profile_enable(False)
     totals = _lib.profile_totals()
     # keep the GPUs under the same load until nvidia-smi has had time to take a few samples (every
@@ -399,7 +424,7 @@ def main_gpu(args, wl):
             "config": {"workload": args.workload, "points_per_gpu": n, "edges_per_gpu": n_edges,
                        "frames_per_gpu": n_frames, "k": wl["k"], "layers": wl["layers"], "channels": wl["channels"],
                        "edge_attr": "relative_position (De=2)", "aggr": "max", "parallelism": f"dp{world} (frames)",
-                       "l2": "256 MiB memset between steps (untimed)", "collective": "loss all-reduce (NCCL)" if world > 1 else "none"},
+                       "l2": "256 MiB memset between steps (untimed)", "launch": "eager" if graph is None else "cuda-graph replay of the step's kernels", "collective": "loss all-reduce (NCCL)" if world > 1 else "none"},
             "e2e": {"value": total_edges * e2e_steps / t_e2e, "unit": "edges/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / e2e_steps * 1e3,
                     "api": "rgnn_pipeline_forward_host (pinned host buffers)"},
@@ -428,6 +453,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

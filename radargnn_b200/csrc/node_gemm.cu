@@ -294,6 +294,11 @@ node_gemm_kernel(TcGemmParams p) {
   // ---- one-time setup, part 1 (no global loads): barriers, TMEM, panel table ----------------------
   long long t_entry = 0;
   if (p.trace != nullptr && blockIdx.x == 0 && tid == 0) t_entry = clock64();
+  if (p.trace != nullptr && tid == 0 && blockIdx.x < 192) {   // debug: per-CTA lifetime in ns (trace[256 + 2 b + {0, 1}])
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[256 + 2 * blockIdx.x] = static_cast<long long>(gt);
+  }
   if (tid == 0) {
     for (int i = 0; i < kMaxRaw; ++i) { mbar_init(&raw_full[i], kLoaderThreads); mbar_init(&raw_empty[i], kConvGroupThreads); }
     for (int i = 0; i < kMaxAStages; ++i) { mbar_init(&a_full[i], kConvGroupThreads); mbar_init(&a_empty[i], 1); }
@@ -364,7 +369,35 @@ node_gemm_kernel(TcGemmParams p) {
       }
     };
     if (total > 0) tile_rows(0);
+    // L2 prefetch of a whole tile's operands with bulk prefetches (one instruction per contiguous region,
+    // no shared memory, no registers): the ring only keeps 48 - 96 KB per SM in flight, DRAM latency under
+    // load needs more, so the tiles two ahead are pulled into L2 and the ring's copies become L2 hits
+    auto l2_prefetch_tile = [&](int t) {
+      if (t >= my_tiles) return;
+      const int64_t tile = blockIdx.x + static_cast<int64_t>(t) * gridDim.x;
+      const int64_t row0 = tile * kRows;
+      const uint32_t rows = static_cast<uint32_t>(p.m - row0 < kRows ? p.m - row0 : kRows);
+      if (p.a1_rows == nullptr && (p.lda1 & 3) == 0) {
+        const float* a = p.a1 + row0 * p.lda1;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(rows * static_cast<uint32_t>(p.lda1) * 4u) : "memory");
+      }
+      if (p.a2 != nullptr) {
+        if (p.a2_panel_major) {
+          const float* a = p.a2 + tile * (static_cast<int64_t>(p.k2 >> 5) << 12);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(static_cast<uint32_t>(p.k2 >> 5) * kABufFloats * 4u) : "memory");
+        } else if ((p.lda2 & 3) == 0) {
+          const float* a = p.a2 + row0 * p.lda2;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(rows * static_cast<uint32_t>(p.lda2) * 4u) : "memory");
+        }
+      }
+      if (p.at != nullptr && (p.ldat & 3) == 0) {
+        const float* a = p.at + row0 * p.ldat;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(rows * static_cast<uint32_t>(p.ldat) * 4u) : "memory");
+      }
+    };
+    if (tid == 0) { l2_prefetch_tile(1); l2_prefetch_tile(2); }
     for (int g = 0; g < total; ++g) {
+      if (tid == 0 && pi == 0) l2_prefetch_tile(tl + 3);
       if (trace != nullptr && tid == 0 && pi == 0 && tl < 32) trace[0 * 64 + tl * 2] = clock64();
       if (wrap >= 1u && !mbar_wait(&raw_empty[slot], (wrap - 1u) & 1u)) timed_out = true;
       const PanelInfo& info = s.panel[pi];
@@ -799,6 +832,11 @@ node_gemm_kernel(TcGemmParams p) {
 
   if (trace != nullptr && tid == 0) trace[3 * 64 + 1] = clock64();
   if (timed_out && p.status != nullptr) atomicExch(p.status, RGNN_ERR_CUDA);
+  if (p.trace != nullptr && tid == 0 && blockIdx.x < 192) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[256 + 2 * blockIdx.x + 1] = static_cast<long long>(gt);
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == kMmaWarp) {

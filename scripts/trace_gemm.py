@@ -15,14 +15,18 @@ cfg = make_cfg()
 for _ in range(3):
     ops.pipeline_forward(cfg, pos, vel, x0)
 for tag in (b"node_gemm_pre", b"node_gemm_post", b"node_gemm_pre@2", b"node_gemm_post@2"):
-    buf = torch.zeros(4 * 64, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(4 * 64 + 2 * 192, dtype=torch.int64, device="cuda")
     fn(buf.data_ptr(), tag)
     ops.pipeline_forward(cfg, pos, vel, x0)
     torch.cuda.synchronize()
-    t = buf.cpu().numpy().reshape(4, 32, 2)
+    life = buf.cpu().numpy()[256:].reshape(192, 2)
+    life = life[life[:, 0] > 0]
+    t = buf.cpu().numpy()[:256].reshape(4, 32, 2)
     t0 = t[3, 0, 0]
     print(tag.decode(), "kernel cycles (CTA 0):", t[3, 0, 1] - t0, " setup part 1 cycles:", t0 - buf.cpu().numpy()[3 * 64 + 63])
     tag = tag.split(b"@")[0]
+    st, en = life[:, 0] - life[:, 0].min(), life[:, 1] - life[:, 0].min()
+    print(f"  CTAs {len(life)}: start spread {int(st.max())} ns, durations min/median/max {int((en-st).min())}/{int(np.median(en-st))}/{int((en-st).max())} ns, last end {int(en.max())} ns")
     for tl in range(8):
         if t[0, tl, 0] == 0: break
         row = [int(v - t0) for v in (t[0, tl, 0], t[0, tl, 1], t[1, tl, 0], t[1, tl, 1], t[2, tl, 0], t[2, tl, 1])]
