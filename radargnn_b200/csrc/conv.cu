@@ -289,33 +289,37 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
     beg = 0; deg = 0;
     if (pass < kPasses && row < row_end) { beg = csc_ptr[row]; deg = csc_ptr[row + 1] - beg; }
   };
-  auto load_slots = [&](int beg, int deg, int b, SlotRegs& r) {
+  // source indices of the lane's slots: needed to issue the gathers, prefetched one pass ahead
+  auto load_src = [&](int beg, int deg, int b, int (&src)[kHold]) {
+#pragma unroll
+    for (int h = 0; h < kHold; ++h) src[h] = (b + 8 * h + q < deg) ? csc_src[beg + b + 8 * h + q] : 0;
+  };
+  // edge attributes of the lane's slots: first used after the pass's first gathers have landed, so they are
+  // loaded in the pass itself (zero for slots beyond the row's degree)
+  auto load_attr = [&](int beg, int deg, int b, float (&e)[kHold][DE]) {
 #pragma unroll
     for (int h = 0; h < kHold; ++h) {
-      r.src[h] = 0;
+      const bool on = b + 8 * h + q < deg;
+      const float* ep = ea + static_cast<int64_t>(beg + b + 8 * h + q) * DE;
 #pragma unroll
-      for (int d = 0; d < DE; ++d) r.e[h][d] = 0.f;
-      if (b + 8 * h + q < deg) {
-        const int slot = beg + b + 8 * h + q;
-        r.src[h] = csc_src[slot];
-        const float* e = ea + static_cast<int64_t>(slot) * DE;
-#pragma unroll
-        for (int d = 0; d < DE; ++d) r.e[h][d] = e[d];
-      }
+      for (int d = 0; d < DE; ++d) e[h][d] = on ? ep[d] : 0.f;
     }
   };
   int beg, deg, beg1, deg1, beg2, deg2;
   load_ptr(0, beg, deg);
   load_ptr(1, beg1, deg1);
-  SlotRegs pre;
-  load_slots(beg, deg, 0, pre);
+  int pre_src[kHold];
+  load_src(beg, deg, 0, pre_src);
 
   for (int it = 0; it < kPasses; ++it) {
     const int row = row_base + it * kSplitPassRows;
     const bool live = row < row_end;
     load_ptr(it + 2, beg2, deg2);
-    SlotRegs cur = pre;
-    load_slots(beg1, deg1, 0, pre);   // next pass (zeros past the last pass)
+    SlotRegs cur;
+#pragma unroll
+    for (int h = 0; h < kHold; ++h) cur.src[h] = pre_src[h];
+    load_attr(beg, deg, 0, cur.e);
+    load_src(beg1, deg1, 0, pre_src);   // next pass (zeros past the last pass)
     const int nmax = __reduce_max_sync(0xffffffffu, deg);
     float4 acc[4] = {init4, init4, init4, init4};
     float4 tacc = init4;
@@ -325,7 +329,7 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[u][i] = init4;
     for (int b = 0; b < nmax; b += 8 * kHold) {
-      if (b > 0) load_slots(beg, deg, b, cur);   // in-degree above 32: not prefetched
+      if (b > 0) { load_src(beg, deg, b, cur.src); load_attr(beg, deg, b, cur.e); }   // in-degree above 32: not prefetched
       // tail channels, slot-parallel: issue the narrow gathers now, use them after the first main group
       float4 tl[kHold];
 #pragma unroll
