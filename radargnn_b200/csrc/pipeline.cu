@@ -87,6 +87,24 @@ int carve(ArenaT& a, const rgnn_pipeline_desc* d, int64_t n, int32_t n_frames, i
   return RGNN_OK;
 }
 
+// side stream + events of the host-buffer entry point, one set per device
+struct HostPathStreams { cudaStream_t copy; cudaEvent_t start, x0_ready, graph_done, copies_done; bool ok; };
+HostPathStreams* host_path_streams() {
+  static HostPathStreams per_device[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  HostPathStreams& h = per_device[dev];
+  if (!h.ok) {
+    if (cudaStreamCreateWithFlags(&h.copy, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&h.start, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h.x0_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h.graph_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h.copies_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    h.ok = true;
+  }
+  return &h;
+}
+
 }  // namespace
 }  // namespace rgnn
 
@@ -104,11 +122,15 @@ size_t rgnn_pipeline_workspace_bytes(const rgnn_pipeline_desc* desc, int64_t n_p
   return a.used;
 }
 
-int rgnn_pipeline_forward(const rgnn_pipeline_desc* desc, const float* pos, const float* vel, const float* x0,
-                          const int64_t* frame_ptr_host, int32_t n_frames, int64_t* edge_index, int64_t n_edges,
-                          float* edge_attr, float* h, int32_t* error_flag, void* workspace,
-                          size_t workspace_bytes, rgnn_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+}  // extern "C"
+
+// x0_ready (optional): event the stream waits for before the first layer reads x0; graph_done (optional):
+// recorded once edge_index / edge_attr are final -- the host entry point overlaps its copies with them
+static int pipeline_forward_impl(const rgnn_pipeline_desc* desc, const float* pos, const float* vel, const float* x0,
+                                 const int64_t* frame_ptr_host, int32_t n_frames, int64_t* edge_index, int64_t n_edges,
+                                 float* edge_attr, float* h, int32_t* error_flag, void* workspace,
+                                 size_t workspace_bytes, cudaStream_t stream, cudaEvent_t x0_ready, cudaEvent_t graph_done) {
+  rgnn_stream_t stream_ = static_cast<rgnn_stream_t>(stream);
   int32_t de = 0, c_max = 0;
   RGNN_RETURN_IF_ERROR(validate(desc, &de, &c_max));
   if (frame_ptr_host == nullptr || n_frames < 1 || frame_ptr_host[0] != 0 || n_edges < 0) return RGNN_ERR_INVALID_ARGUMENT;
@@ -178,6 +200,9 @@ int rgnn_pipeline_forward(const rgnn_pipeline_desc* desc, const float* pos, cons
   RGNN_RETURN_IF_ERROR(gather_edge_rows(edge_attr, w.csc_eid, n_edges, de, w.ea_csc, stream));
   }
 
+  if (graph_done != nullptr) RGNN_CUDA_CHECK(cudaEventRecord(graph_done, stream));
+  if (x0_ready != nullptr) RGNN_CUDA_CHECK(cudaStreamWaitEvent(stream, x0_ready, 0));
+
   // ---- 4. conv -> BatchNorm(train) -> ReLU, L times ------------------------------------------
   ConvInput in;
   in.x = x0; in.ldx = desc->layers[0].in_channels;
@@ -210,6 +235,16 @@ int rgnn_pipeline_forward(const rgnn_pipeline_desc* desc, const float* pos, cons
   const int32_t c_last = desc->layers[desc->n_layers - 1].out_channels;
   // last BatchNorm + ReLU, scattered back to the caller's node order
   return bn_apply(in.x, in.ldx, n, c_last, in.mean, in.scale, in.beta, 1, h, c_last, stream, w.graph.sorted_idx);
+}
+
+extern "C" {
+
+int rgnn_pipeline_forward(const rgnn_pipeline_desc* desc, const float* pos, const float* vel, const float* x0,
+                          const int64_t* frame_ptr_host, int32_t n_frames, int64_t* edge_index, int64_t n_edges,
+                          float* edge_attr, float* h, int32_t* error_flag, void* workspace,
+                          size_t workspace_bytes, rgnn_stream_t stream_) {
+  return pipeline_forward_impl(desc, pos, vel, x0, frame_ptr_host, n_frames, edge_index, n_edges, edge_attr, h, error_flag,
+                               workspace, workspace_bytes, static_cast<cudaStream_t>(stream_), nullptr, nullptr);
 }
 
 size_t rgnn_pipeline_host_workspace_bytes(const rgnn_pipeline_desc* desc, int64_t n_points, int32_t n_frames,
@@ -255,18 +290,31 @@ int rgnn_pipeline_forward_host(const rgnn_pipeline_desc* desc, const float* pos_
   const size_t inner = rgnn_pipeline_workspace_bytes(desc, n, n_frames, n_edges);
   char* inner_ws = a.take<char>(inner);
   if (a.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  // Copies overlap the compute: x0 (the bulk of the input) travels on a side stream while the main stream
+  // builds the graph, and edge_index / edge_attr travel back while the layers run.
+  HostPathStreams* hs = host_path_streams();
+  if (hs == nullptr) return RGNN_ERR_CUDA;
   if (n > 0) {
     RGNN_CUDA_CHECK(cudaMemcpyAsync(pos, pos_host, sizeof(float) * n * 2, cudaMemcpyHostToDevice, stream));
     RGNN_CUDA_CHECK(cudaMemcpyAsync(vel, vel_host, sizeof(float) * n * 2, cudaMemcpyHostToDevice, stream));
-    RGNN_CUDA_CHECK(cudaMemcpyAsync(x0, x0_host, sizeof(float) * n * c0, cudaMemcpyHostToDevice, stream));
+    RGNN_CUDA_CHECK(cudaEventRecord(hs->start, stream));                 // orders the side stream after earlier work
+    RGNN_CUDA_CHECK(cudaStreamWaitEvent(hs->copy, hs->start, 0));
+    RGNN_CUDA_CHECK(cudaMemcpyAsync(x0, x0_host, sizeof(float) * n * c0, cudaMemcpyHostToDevice, hs->copy));
+    RGNN_CUDA_CHECK(cudaEventRecord(hs->x0_ready, hs->copy));
   }
-  RGNN_RETURN_IF_ERROR(rgnn_pipeline_forward(desc, pos, vel, x0, frame_ptr_host, n_frames, edge_index, n_edges,
-                                             edge_attr, h, flag, inner_ws, inner, stream_));
+  RGNN_RETURN_IF_ERROR(pipeline_forward_impl(desc, pos, vel, x0, frame_ptr_host, n_frames, edge_index, n_edges,
+                                             edge_attr, h, flag, inner_ws, inner, stream, n > 0 ? hs->x0_ready : nullptr,
+                                             n > 0 ? hs->graph_done : nullptr));
   int32_t flag_host = 0;
-  if (edge_index_host != nullptr && n_edges > 0)
-    RGNN_CUDA_CHECK(cudaMemcpyAsync(edge_index_host, edge_index, sizeof(int64_t) * n_edges * 2, cudaMemcpyDeviceToHost, stream));
-  if (edge_attr_host != nullptr && n_edges > 0 && de > 0)
-    RGNN_CUDA_CHECK(cudaMemcpyAsync(edge_attr_host, edge_attr, sizeof(float) * n_edges * de, cudaMemcpyDeviceToHost, stream));
+  if (n > 0) {
+    RGNN_CUDA_CHECK(cudaStreamWaitEvent(hs->copy, hs->graph_done, 0));
+    if (edge_index_host != nullptr && n_edges > 0)
+      RGNN_CUDA_CHECK(cudaMemcpyAsync(edge_index_host, edge_index, sizeof(int64_t) * n_edges * 2, cudaMemcpyDeviceToHost, hs->copy));
+    if (edge_attr_host != nullptr && n_edges > 0 && de > 0)
+      RGNN_CUDA_CHECK(cudaMemcpyAsync(edge_attr_host, edge_attr, sizeof(float) * n_edges * de, cudaMemcpyDeviceToHost, hs->copy));
+    RGNN_CUDA_CHECK(cudaEventRecord(hs->copies_done, hs->copy));
+    RGNN_CUDA_CHECK(cudaStreamWaitEvent(stream, hs->copies_done, 0));
+  }
   if (h_host != nullptr && n > 0)
     RGNN_CUDA_CHECK(cudaMemcpyAsync(h_host, h, sizeof(float) * n * c_last, cudaMemcpyDeviceToHost, stream));
   RGNN_CUDA_CHECK(cudaMemcpyAsync(&flag_host, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
