@@ -192,7 +192,7 @@ constexpr int kGemmThreads = (kMmaWarp + 1) * 32;
 constexpr int kMaxPanels = 16;
 constexpr int kAStageCols = 64;                   // TMEM columns of one A stage: 32 hi + 32 lo
 
-enum PanelFlags : int32_t { kPanelBn = 1, kPanelRelu = 2, kPanelRowScale = 4, kPanelGather = 8, kPanelBulk = 16 };
+enum PanelFlags : int32_t { kPanelBn = 1, kPanelRelu = 2, kPanelRowScale = 4, kPanelGather = 8, kPanelBulk = 16, kPanelTmaA1 = 32, kPanelTmaAt = 64 };
 
 struct PanelInfo {
   const float* base;   // segment base pointer (column 0 of the segment)
@@ -273,7 +273,7 @@ __device__ __forceinline__ void umma_tf32_ts_pred(uint32_t tmem_d, uint32_t tmem
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
-node_gemm_kernel(TcGemmParams p) {
+node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int np = p.np, kp = p.kp, kp32 = (p.kp + 31) & ~31;
   const int a_stages = p.a_stages, raw_slots = p.raw_slots;
@@ -318,7 +318,7 @@ node_gemm_kernel(TcGemmParams p) {
     const int k0 = tid * kKc;
     PanelInfo pi;
     const int a1_flags = (p.a1_mean != nullptr ? kPanelBn : 0) | (p.relu_a1 ? kPanelRelu : 0) |
-                         (p.a1_rows != nullptr ? kPanelGather : 0);
+                         (p.a1_rows != nullptr ? kPanelGather : 0) | (p.a1_tma ? kPanelTmaA1 : 0);
     if (k0 < k1p) {
       pi.base = p.a1; pi.ld = p.lda1; pi.col0 = k0; pi.valid = min(32, p.k1 - k0); pi.flags = a1_flags;
     } else if (k0 < k1p + k2p) {
@@ -327,7 +327,7 @@ node_gemm_kernel(TcGemmParams p) {
       if (p.a2_panel_major) { pi.flags |= kPanelBulk; pi.ld = p.k2 >> 5; }   // ld = panels per tile
     } else if (k0 < k1p + k2p + ktp) {
       pi.base = p.at; pi.ld = p.ldat; pi.col0 = k0 - k1p - k2p; pi.valid = min(32, p.kt - pi.col0);
-      pi.flags = p.relu_a2 ? kPanelRelu : 0;
+      pi.flags = (p.relu_a2 ? kPanelRelu : 0) | (p.at_tma ? kPanelTmaAt : 0);
     } else {
       pi.base = p.a1; pi.ld = p.lda1; pi.col0 = k0 - k1p - k2p - ktp; pi.valid = min(32, p.k3 - pi.col0);
       pi.flags = a1_flags | kPanelRowScale;
@@ -417,6 +417,18 @@ node_gemm_kernel(TcGemmParams p) {
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kABufFloats * 4u) : "memory");
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                        ::"r"(slot_addr), "l"(src), "r"(kABufFloats * 4u), "r"(bar) : "memory");
+        } else {
+          mbar_arrive(&raw_full[slot]);
+        }
+      } else if (info.flags & (kPanelTmaA1 | kPanelTmaAt)) {
+        // row-major operand through the tensor-memory accelerator: one 2-D tile load per panel, written in
+        // the ring's 128-byte-swizzled layout, rows / columns outside the tensor zero-filled
+        if (tid == 0) {
+          const uint64_t tmap = reinterpret_cast<uint64_t>((info.flags & kPanelTmaA1) ? &p.tm_a1 : &p.tm_at);
+          const uint32_t bar = smem_u32(&raw_full[slot]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kABufFloats * 4u) : "memory");
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                       ::"r"(slot_addr), "l"(tmap), "r"(info.col0), "r"(row0), "r"(bar) : "memory");
         } else {
           mbar_arrive(&raw_full[slot]);
         }
@@ -917,6 +929,38 @@ extern "C" void rgnn_debug_trace_node_gemm(void* device_buffer, const char* tag)
   if (at != nullptr) { g_trace_skip = atoi(at + 1); *at = 0; }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// row-major [rows, cols] fp32 tensor (row stride ld floats), box = one panel: 32 floats x 128 rows
+static bool encode_panel_map(CUtensorMap* tm, const float* base, int64_t rows, int32_t cols, int64_t ld) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr || base == nullptr || rows <= 0 || cols <= 0) return false;
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0 || (ld * 4) % 16 != 0) return false;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 4};
+  const cuuint32_t box[2] = {32, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
   if (p.m <= 0) return RGNN_OK;
   if (g_trace_buffer != nullptr && strcmp(tag, g_trace_tag) == 0 && g_trace_skip-- <= 0) { p.trace = g_trace_buffer; g_trace_buffer = nullptr; }
@@ -942,6 +986,13 @@ int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
   p.raw_slots = p.raw_slots / p.conv_groups * p.conv_groups;
   p.a_stages = p.a_stages / p.conv_groups * p.conv_groups;
   if (p.y2 != nullptr && (!p.staged_epilogue || (p.n_split & 3) != 0 || (p.ldy2 & 3) != 0)) return RGNN_ERR_UNSUPPORTED;
+  // row-major operands go through TMA when they are plain (no gather map) and 16-byte aligned
+  static int tma_enabled = -1;
+  if (tma_enabled < 0) { const char* e = getenv("RGNN_DISABLE_TMA"); tma_enabled = (e != nullptr && e[0] == '1') ? 0 : 1; }
+  memset(&p.tm_a1, 0, sizeof(p.tm_a1));
+  memset(&p.tm_at, 0, sizeof(p.tm_at));
+  p.a1_tma = (tma_enabled && p.a1_rows == nullptr && encode_panel_map(&p.tm_a1, p.a1, p.m, p.k1, p.lda1)) ? 1 : 0;
+  p.at_tma = (tma_enabled && p.at != nullptr && p.kt > 0 && encode_panel_map(&p.tm_at, p.at, p.m, p.kt, p.ldat)) ? 1 : 0;
   const size_t smem = smem_bytes_for(p.np, p.kp, p.raw_slots, p.staged_epilogue);
   static size_t configured = 0;
   if (smem > configured) {

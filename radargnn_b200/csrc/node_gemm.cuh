@@ -1,6 +1,7 @@
 // node_gemm.cuh -- internal interface of the tcgen05 node contraction (node_gemm.cu).
 #pragma once
 
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -54,6 +55,11 @@ struct TcGemmParams {
   int64_t m = 0;
   int32_t* status = nullptr;                                     // device flag set if a barrier wait timed out
   long long* trace = nullptr;                                    // debug timeline of CTA 0 (node_gemm.cu)
+  // TMA descriptors (filled by launch_tc_gemm): a1 / a_tail as 2-D row-major tensors, box = one panel
+  // (32 floats x 128 rows, 128-byte swizzle, zero fill outside the tensor)
+  int32_t a1_tma = 0, at_tma = 0;
+  alignas(64) CUtensorMap tm_a1;
+  alignas(64) CUtensorMap tm_at;
 };
 
 // float offset of element (row, col) of a panel-major operand with `panels` 32-float panels per 128-row tile
