@@ -73,19 +73,22 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 
-// bounded wait: a lost arrival must not hang the GPU (returns false on timeout)
+// Bounded wait: a lost arrival must not hang the GPU (returns false on timeout).  try_wait carries a
+// suspend-time hint: the warp sleeps in hardware until the phase completes (it is woken by the arrival) or
+// the hint expires, instead of re-issuing the poll -- with ~20 warps parked on barriers at any time, hot
+// polling took the issue slots of the few warps that had work (every role ran at ~15 cycles/instruction).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  for (int it = 0; it < (1 << 22); ++it) {
+  for (int it = 0; it < (1 << 18); ++it) {
     uint32_t done;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(20000u)
         : "memory");
     if (done) return true;
   }
@@ -460,7 +463,6 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     const int k1r = (p.k1 + 3) & ~3;
     const float* rawrow = s.raw + rl * 32;
     const int sw = rl & 7;
-    const bool tracer = trace != nullptr && tid == kLoaderThreads;
     // A waiter may be at most one barrier phase ahead of the phase in flight (the parity test cannot tell
     // two phases apart) and panels do not complete in issue order (bulk copies vs. cp.async), so the host
     // makes the ring slot and TMEM stage counts multiples of the group count: a slot / stage is then always
@@ -476,9 +478,7 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     for (int g = grp; g < total && grp < n_groups; g += n_groups) {
       const PanelInfo& info = s.panel[pi];
       const int flags = info.flags & (kPanelBn | kPanelRelu | kPanelRowScale);
-      if (tracer && g < 45) trace[3 * 64 + 2 + (g / 3) * 4] = clock64();
       if (!mbar_wait(&raw_full[slot], raw_round & 1u)) timed_out = true;
-      if (tracer && g < 45) trace[3 * 64 + 3 + (g / 3) * 4] = clock64();
       const float* src = rawrow + static_cast<size_t>(slot) * kABufFloats;
       float4 v[8];
 #pragma unroll
@@ -537,7 +537,6 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&a_full[stg]);
-      if (tracer && g < 45) trace[3 * 64 + 4 + (g / 3) * 4] = clock64();
       pi += n_groups; while (pi >= panels) { pi -= panels; ++tl; }
       slot += n_groups; while (slot >= raw_slots) { slot -= raw_slots; ++raw_round; }
       stg += n_groups; while (stg >= a_stages) { stg -= a_stages; ++a_round; }
@@ -648,6 +647,8 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         const int rows_valid = static_cast<int>(p.m - tile_row0 < 32 ? p.m - tile_row0 : 32);
         const int c4 = lane & 7, rsub = lane >> 3;
         for (int cd = half; cd < n_dbl; cd += 2) {
+          const bool etr = trace != nullptr && et == 0 && tl == 2 && (cd >> 1) < 5;   // debug: block timeline of one warp
+          if (etr) trace[3 * 64 + 2 + (cd >> 1) * 4] = clock64();
           const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ab * acc_stride + cd * 32);
           float* strow = st + lane * 36;
           if (cd * 2 + 1 < n_blocks) {
@@ -676,6 +677,7 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
               *reinterpret_cast<uint4*>(strow + j4 * 4) = make_uint4(r[j4 * 4], r[j4 * 4 + 1], r[j4 * 4 + 2], r[j4 * 4 + 3]);
           }
           __syncwarp();
+          if (etr) trace[3 * 64 + 3 + (cd >> 1) * 4] = clock64();
           const int col = cd * 32 + c4 * 4;
           float4 csum4 = make_float4(0.f, 0.f, 0.f, 0.f), csq4 = csum4;
           if (col < p.n_store && col < np) {
@@ -742,6 +744,7 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
               *reinterpret_cast<float4*>(csq + col) = csq4;
             }
           }
+          if (etr) trace[3 * 64 + 4 + (cd >> 1) * 4] = clock64();
           __syncwarp();
         }
       } else
@@ -844,13 +847,14 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
 
   if (trace != nullptr && tid == 0) trace[3 * 64 + 1] = clock64();
   if (timed_out && p.status != nullptr) atomicExch(p.status, RGNN_ERR_CUDA);
-  if (p.trace != nullptr && tid == 0 && blockIdx.x < 192) {
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (p.trace != nullptr && tid == 0 && blockIdx.x < 192) {   // debug: all roles of the CTA are done
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     p.trace[256 + 2 * blockIdx.x + 1] = static_cast<long long>(gt);
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
   }

@@ -34,4 +34,4 @@ for tag in (b"node_gemm_pre", b"node_gemm_post", b"node_gemm_pre@2", b"node_gemm
     f = buf.cpu().numpy()[3 * 64 + 2: 3 * 64 + 62].reshape(15, 4)
     for g in range(15):
         if f[g, 0] == 0: break
-        print(f"  converter panel {2*g:2d}: start {int(f[g,0]-t0):7d}  raw-wait {int(f[g,1]-f[g,0]):6d}  convert+st {int(f[g,2]-f[g,1]):6d}")
+        print(f"  epilogue warp 0, tile 2, block {g}: start {int(f[g,0]-t0):7d}  tmem-ld+sts {int(f[g,1]-f[g,0]):6d}  stores {int(f[g,2]-f[g,1]):6d}")
