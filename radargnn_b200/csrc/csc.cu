@@ -111,6 +111,69 @@ int csc_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, bool 
   return RGNN_OK;
 }
 
+// k-NN pipeline variant: one thread per (cell-sorted query, neighbour slot)
+template <int DIMS>
+__global__ void __launch_bounds__(256)
+fill_slots_features_knn_kernel(const int64_t* __restrict__ edge_index, int64_t n_edges, int64_t n_points, int k,
+                               const int32_t* __restrict__ sorted_idx, const int32_t* __restrict__ sorted_frame,
+                               const FrameGrid* __restrict__ grids, const int32_t* __restrict__ rank,
+                               const float* __restrict__ sorted_pts, const int32_t* __restrict__ csc_ptr,
+                               int32_t* __restrict__ cursor, int32_t* __restrict__ csc_src,
+                               int32_t* __restrict__ csc_eid, bool need_vel, FusedEdgeAttr f) {
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t qs = tid / k;
+  if (qs >= n_points) return;
+  const int jj = static_cast<int>(tid - qs * k);
+  const FrameGrid g = grids[sorted_frame[qs]];
+  if (!g.active) return;   // frames that took no part in the search have no edges
+  const int64_t i = sorted_idx[qs];
+  const int64_t e = g.edge_off + (i - g.pt_begin) * k + jj;
+  const int64_t j = edge_index[n_edges + e];
+  const int t = rank[j];   // the one scattered lookup left: neighbour id -> sorted position
+  const int slot = csc_ptr[t] + atomicAdd(&cursor[t], 1);
+  csc_eid[slot] = static_cast<int32_t>(e);
+  csc_src[slot] = static_cast<int32_t>(qs);
+  double xi[4], xj[4], vi[4] = {0.0, 0.0, 0.0, 0.0}, vj[4] = {0.0, 0.0, 0.0, 0.0};
+  if (DIMS == 2) {
+    efm::load_vec(sorted_pts, qs, 2, xi);
+    efm::load_vec(sorted_pts, static_cast<int64_t>(t), 2, xj);
+    if (need_vel) { efm::load_vec(f.vel, i, 2, vi); efm::load_vec(f.vel, j, 2, vj); }
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(sorted_pts + qs * 4);
+    const float4 b = *reinterpret_cast<const float4*>(sorted_pts + static_cast<int64_t>(t) * 4);
+    xi[0] = a.x; xi[1] = a.y; xi[2] = xi[3] = 0.0; vi[0] = a.z; vi[1] = a.w;
+    xj[0] = b.x; xj[1] = b.y; xj[2] = xj[3] = 0.0; vj[0] = b.z; vj[1] = b.w;
+  }
+  efm::write_edge_row<float>(xi, xj, vi, vj, 2, 2, f.spec, f.error_flag, f.edge_attr + e * f.spec.width,
+                             f.ea_csc + static_cast<int64_t>(slot) * f.spec.width);
+}
+
+int csc_build_fused_knn(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int32_t k, int32_t dims,
+                        const GraphWorkspace& graph, const CscWorkspace& w, int32_t* csc_ptr, int32_t* csc_src,
+                        int32_t* csc_eid, cudaStream_t stream, const FusedEdgeAttr& fea) {
+  RGNN_PROFILE("csc_build_edge_attr", stream);
+  RGNN_RETURN_IF_ERROR(exclusive_scan_i32(w.count, csc_ptr, n_nodes, w.scan_scratch, stream));
+  if (n_edges == 0) return RGNN_OK;
+  RGNN_CUDA_CHECK(cudaMemsetAsync(w.cursor, 0, sizeof(int32_t) * (n_nodes + 1), stream));
+  bool need_vel = false;
+  for (int i = 0; i < fea.spec.n; ++i) {
+    const int ft = fea.spec.feature[i];
+    if (ft == RGNN_EF_POINT_PAIR_FEATURES || ft == RGNN_EF_VELOCITY_EUCLIDEAN_DISTANCE || ft == RGNN_EF_RELATIVE_VELOCITY) need_vel = true;
+  }
+  const unsigned blocks = div_up(n_nodes * k, 256);
+  const float* pts = static_cast<const float*>(graph.sorted_pts);
+  if (dims == 2)
+    fill_slots_features_knn_kernel<2><<<blocks, 256, 0, stream>>>(edge_index, n_edges, n_nodes, k, graph.sorted_idx, graph.sorted_frame,
+                                                                   graph.grids, graph.rank, pts, csc_ptr, w.cursor, csc_src, csc_eid,
+                                                                   need_vel, fea);
+  else
+    fill_slots_features_knn_kernel<4><<<blocks, 256, 0, stream>>>(edge_index, n_edges, n_nodes, k, graph.sorted_idx, graph.sorted_frame,
+                                                                   graph.grids, graph.rank, pts, csc_ptr, w.cursor, csc_src, csc_eid,
+                                                                   need_vel, fea);
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
+}
+
 int csc_build_fused(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, bool counts_ready,
                     const CscWorkspace& w, int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid, cudaStream_t stream,
                     const int32_t* node_map, const FusedEdgeAttr& fea) {

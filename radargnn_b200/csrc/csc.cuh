@@ -3,6 +3,7 @@
 
 #include "common.cuh"
 #include "features.cuh"
+#include "graph_build.cuh"
 
 namespace rgnn {
 
@@ -43,5 +44,15 @@ struct FusedEdgeAttr {
 int csc_build_fused(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, bool counts_ready,
                     const CscWorkspace& w, int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid, cudaStream_t stream,
                     const int32_t* node_map, const FusedEdgeAttr& fea);
+
+// Same result for the k-NN graph the pipeline has just built (edge rows i*k .. i*k+k-1 per query i), but the
+// edges are visited per CELL-SORTED query: the targets of neighbouring threads are neighbours in the sorted
+// node order, so the row-pointer / cursor / slot / position accesses are local instead of one lone 32-byte
+// sector each; the source of every edge is the query's own sorted position (no lookup).  Requires
+// counts_ready (the k-NN kernel's in-degree histogram) and f32 [N, 2] sorted positions (distance_dims == 2)
+// or [N, 4] = [pos | vel] (distance_dims == 4) in graph.sorted_pts.
+int csc_build_fused_knn(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int32_t k, int32_t dims,
+                        const GraphWorkspace& graph, const CscWorkspace& w, int32_t* csc_ptr, int32_t* csc_src,
+                        int32_t* csc_eid, cudaStream_t stream, const FusedEdgeAttr& fea);
 
 }  // namespace rgnn

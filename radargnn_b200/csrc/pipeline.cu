@@ -188,8 +188,12 @@ static int pipeline_forward_impl(const rgnn_pipeline_desc* desc, const float* po
     // attributes in both orders (conv stack in CELL-SORTED node order, see below)
     FusedEdgeAttr fea;
     fea.pos = pos; fea.vel = vel; fea.spec = spec; fea.edge_attr = edge_attr; fea.ea_csc = w.ea_csc; fea.error_flag = error_flag;
-    RGNN_RETURN_IF_ERROR(csc_build_fused(edge_index, n_edges, n, counts_ready, w.csc, w.csc_ptr, w.csc_src, w.csc_eid,
-                                         stream, w.graph.rank, fea));
+    if (desc->search == 0 && counts_ready)
+      RGNN_RETURN_IF_ERROR(csc_build_fused_knn(edge_index, n_edges, n, desc->k, desc->distance_dims, w.graph, w.csc,
+                                               w.csc_ptr, w.csc_src, w.csc_eid, stream, fea));
+    else
+      RGNN_RETURN_IF_ERROR(csc_build_fused(edge_index, n_edges, n, counts_ready, w.csc, w.csc_ptr, w.csc_src, w.csc_eid,
+                                           stream, w.graph.rank, fea));
   } else {
   RGNN_RETURN_IF_ERROR(launch_edge_features(pos, vel, RGNN_F32, 2, 2, edge_index, n_edges, spec, edge_attr, RGNN_F32,
                                             error_flag, stream));
