@@ -12,6 +12,8 @@
 
 #include <vector>
 
+#include <stdlib.h>
+
 #include "graph_build.cuh"
 
 namespace rgnn {
@@ -239,8 +241,10 @@ __device__ __forceinline__ bool cand_less(double d, int id, double wd, int wid) 
 }
 
 // ---- k-NN query: one thread per point, in cell-sorted order ------------------------------
-template <typename T, int DIMS, int KMAX>
-__global__ void __launch_bounds__(128)
+// OCC: resident 128-thread CTAs per SM the kernel is compiled for (register cap); the search is bound by
+// instruction issue at few warps per scheduler, so for k <= 16 the cap is lowered to 80 registers.
+template <typename T, int DIMS, int KMAX, int OCC>
+__global__ void __launch_bounds__(128, OCC)
 knn_query_kernel(const T* __restrict__ sorted_pts, const int32_t* __restrict__ sorted_idx,
                  const int32_t* __restrict__ sorted_cell, const int32_t* __restrict__ sorted_frame,
                  const int32_t* __restrict__ cell_start, const FrameGrid* __restrict__ grids,
@@ -498,15 +502,17 @@ int knn_query_t(int64_t n, int32_t k, int64_t* edge_index, int64_t n_edges, int3
   const unsigned blocks = div_up(n, 128);
   const T* pts = static_cast<const T*>(w.sorted_pts);
   RGNN_PROFILE("knn_query", stream);
-#define RGNN_KNN_LAUNCH(KMAX)                                                                     \
-  knn_query_kernel<T, DIMS, KMAX><<<blocks, 128, 0, stream>>>(pts, w.sorted_idx, w.sorted_cell,   \
+#define RGNN_KNN_LAUNCH(KMAX, OCC)                                                                    \
+  knn_query_kernel<T, DIMS, KMAX, OCC><<<blocks, 128, 0, stream>>>(pts, w.sorted_idx, w.sorted_cell,  \
       w.sorted_frame, w.cell_start, w.grids, n, k, edge_index, n_edges, in_degree, degree_map)
-  if (k <= 4) RGNN_KNN_LAUNCH(4);
-  else if (k <= 8) RGNN_KNN_LAUNCH(8);
-  else if (k <= 16) RGNN_KNN_LAUNCH(16);
-  else if (k <= 24) RGNN_KNN_LAUNCH(24);
-  else if (k <= 32) RGNN_KNN_LAUNCH(32);
-  else RGNN_KNN_LAUNCH(64);
+  static int occ16 = 0;   // RGNN_KNN_OCC = 4 | 6 | 8: experiments on the k <= 16 variant
+  if (occ16 == 0) { const char* e = getenv("RGNN_KNN_OCC"); occ16 = e != nullptr ? atoi(e) : 6; }
+  if (k <= 4) RGNN_KNN_LAUNCH(4, 8);
+  else if (k <= 8) RGNN_KNN_LAUNCH(8, 8);
+  else if (k <= 16) { if (occ16 == 8) RGNN_KNN_LAUNCH(16, 8); else if (occ16 == 4) RGNN_KNN_LAUNCH(16, 4); else RGNN_KNN_LAUNCH(16, 6); }
+  else if (k <= 24) RGNN_KNN_LAUNCH(24, 4);
+  else if (k <= 32) RGNN_KNN_LAUNCH(32, 3);
+  else RGNN_KNN_LAUNCH(64, 2);
 #undef RGNN_KNN_LAUNCH
   RGNN_LAUNCH_CHECK();
   return RGNN_OK;
