@@ -112,8 +112,10 @@ int csc_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, bool 
 }
 
 // k-NN pipeline variant: one thread per (cell-sorted query, neighbour slot)
-template <int DIMS>
-__global__ void __launch_bounds__(256)
+// REL_POS: the edge attributes are exactly [relative_position] (the translation-invariant setting of the
+// shipped configs): two fp64 subtractions, float2 stores, no generic feature interpreter (local memory)
+template <int DIMS, bool REL_POS>
+__global__ void __launch_bounds__(256, REL_POS ? 6 : 3)
 fill_slots_features_knn_kernel(const int64_t* __restrict__ edge_index, int64_t n_edges, int64_t n_points, int k,
                                const int32_t* __restrict__ sorted_idx, const int32_t* __restrict__ sorted_frame,
                                const FrameGrid* __restrict__ grids, const int32_t* __restrict__ rank,
@@ -133,6 +135,16 @@ fill_slots_features_knn_kernel(const int64_t* __restrict__ edge_index, int64_t n
   const int slot = csc_ptr[t] + atomicAdd(&cursor[t], 1);
   csc_eid[slot] = static_cast<int32_t>(e);
   csc_src[slot] = static_cast<int32_t>(qs);
+  if (REL_POS) {
+    const float2 a = *reinterpret_cast<const float2*>(sorted_pts + qs * DIMS);
+    const float2 b = *reinterpret_cast<const float2*>(sorted_pts + static_cast<int64_t>(t) * DIMS);
+    double dx = static_cast<double>(a.x) - static_cast<double>(b.x), dy = static_cast<double>(a.y) - static_cast<double>(b.y);
+    if (f.spec.edge_mode == RGNN_UNDIRECTED) { dx = fabs(dx); dy = fabs(dy); }
+    const float2 o = make_float2(static_cast<float>(dx), static_cast<float>(dy));
+    *reinterpret_cast<float2*>(f.edge_attr + e * 2) = o;
+    *reinterpret_cast<float2*>(f.ea_csc + static_cast<int64_t>(slot) * 2) = o;
+    return;
+  }
   double xi[4], xj[4], vi[4] = {0.0, 0.0, 0.0, 0.0}, vj[4] = {0.0, 0.0, 0.0, 0.0};
   if (DIMS == 2) {
     efm::load_vec(sorted_pts, qs, 2, xi);
@@ -162,14 +174,14 @@ int csc_build_fused_knn(const int64_t* edge_index, int64_t n_edges, int64_t n_no
   }
   const unsigned blocks = div_up(n_nodes * k, 256);
   const float* pts = static_cast<const float*>(graph.sorted_pts);
-  if (dims == 2)
-    fill_slots_features_knn_kernel<2><<<blocks, 256, 0, stream>>>(edge_index, n_edges, n_nodes, k, graph.sorted_idx, graph.sorted_frame,
-                                                                   graph.grids, graph.rank, pts, csc_ptr, w.cursor, csc_src, csc_eid,
-                                                                   need_vel, fea);
-  else
-    fill_slots_features_knn_kernel<4><<<blocks, 256, 0, stream>>>(edge_index, n_edges, n_nodes, k, graph.sorted_idx, graph.sorted_frame,
-                                                                   graph.grids, graph.rank, pts, csc_ptr, w.cursor, csc_src, csc_eid,
-                                                                   need_vel, fea);
+  const bool rel_pos = fea.spec.n == 1 && fea.spec.feature[0] == RGNN_EF_RELATIVE_POSITION && fea.spec.width == 2 &&
+                       reinterpret_cast<uintptr_t>(fea.edge_attr) % 8 == 0 && reinterpret_cast<uintptr_t>(fea.ea_csc) % 8 == 0;
+#define RGNN_FILL_LAUNCH(D, R)                                                                                         \
+  fill_slots_features_knn_kernel<D, R><<<blocks, 256, 0, stream>>>(edge_index, n_edges, n_nodes, k, graph.sorted_idx,  \
+      graph.sorted_frame, graph.grids, graph.rank, pts, csc_ptr, w.cursor, csc_src, csc_eid, need_vel, fea)
+  if (dims == 2) { if (rel_pos) RGNN_FILL_LAUNCH(2, true); else RGNN_FILL_LAUNCH(2, false); }
+  else { if (rel_pos) RGNN_FILL_LAUNCH(4, true); else RGNN_FILL_LAUNCH(4, false); }
+#undef RGNN_FILL_LAUNCH
   RGNN_LAUNCH_CHECK();
   return RGNN_OK;
 }
