@@ -218,8 +218,6 @@ edge_aggregate_kernel(const float* __restrict__ a, const float* __restrict__ b, 
 // (cell-sorted) nodes, 48 at a time: everything an SM gathers concurrently, and from one pass to the
 // next, comes from the same few grid rows, so the L1 working set stays small (more, independent CTAs per
 // SM measured slower: 3 -> 4 -> 5 resident 64-row blocks took 95 -> 116 -> 217 us, L1 thrashing).
-constexpr int kSplitThreads = 384;                      // 12 warps: one persistent CTA per SM (168 registers per thread)
-constexpr int kSplitPassRows = kSplitThreads / 32 * 4;  // rows a CTA works on at a time
 constexpr int kSplitMain = 128;
 
 __device__ __forceinline__ float4 fma4x2(float s, float4 w, float4 a) {
@@ -245,13 +243,15 @@ __device__ __forceinline__ float4 combine4x2(float4 a, float4 v0, float4 v1) {
   return add4(add4(a, v0), v1);
 }
 
-template <int MODE, int DE>
+// kSplitThreads: 384 (12 warps, 168 registers) or 512 (16 warps, 128 registers): one persistent CTA per SM
+template <int MODE, int DE, int kSplitThreads>
 __global__ void __launch_bounds__(kSplitThreads, 1)
 edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restrict__ bt, int p,
                             const float* __restrict__ bias, const float* __restrict__ w_e, int64_t ldwe,
                             const float* __restrict__ ea, const int32_t* __restrict__ csc_ptr,
                             const int32_t* __restrict__ csc_src, int n_nodes, int rows_per_cta,
                             float* __restrict__ out_m, float* __restrict__ out_t, IsolatedNodeTerm iso) {
+  constexpr int kSplitPassRows = kSplitThreads / 32 * 4;  // rows a CTA works on at a time
   constexpr int kW = kSplitMain + 4;             // staged channels: main + one float4 of tail
   __shared__ __align__(16) float ws[DE][kW];     // W_e transposed: ws[d][channel], zero beyond p
   __shared__ __align__(16) float bs[kW];         // message bias, zero beyond p
@@ -277,7 +277,7 @@ edge_aggregate_split_kernel(const float* __restrict__ bm, const float* __restric
   const int row_end = min(n_nodes, row_begin + rows_per_cta);
   const int kPasses = (max(row_end - row_begin, 0) + kSplitPassRows - 1) / kSplitPassRows;
   constexpr bool kOrderFree = MODE == RGNN_AGGR_MAX || MODE == RGNN_AGGR_MIN;
-  constexpr int kHold = 4;                       // slots held per lane: a quarter holds 8 * kHold = 32 slots of its row
+  constexpr int kHold = kSplitThreads > 384 ? 2 : 4;   // slots held per lane: a quarter holds 8 * kHold slots of its row
   const int row_base = row_begin + warp * 4 + quarter;
 
   // Software pipeline over the passes: the row pointers run two passes ahead and the first 32 slots
@@ -469,15 +469,22 @@ int launch_edge_aggregate_split_mode(const float* bm, const float* bt, const Con
                                      const int32_t* csc_src, int64_t n_nodes, float* out_m, float* out_t,
                                      cudaStream_t stream, const IsolatedNodeTerm& iso) {
   // one persistent CTA per SM over a contiguous node range (a multiple of the pass size)
+  static int threads = 0;   // RGNN_AGG_THREADS = 384 | 512 (experiments)
+  if (threads == 0) { const char* e = getenv("RGNN_AGG_THREADS"); threads = (e != nullptr && atoi(e) == 512) ? 512 : 384; }
+  const int pass_rows = threads / 32 * 4;
   const int n = static_cast<int>(n_nodes);
   const int ctas = sm_count();
   int rows_per_cta = static_cast<int>((n_nodes + ctas - 1) / ctas);
-  rows_per_cta = (rows_per_cta + kSplitPassRows - 1) / kSplitPassRows * kSplitPassRows;
+  rows_per_cta = (rows_per_cta + pass_rows - 1) / pass_rows * pass_rows;
   const unsigned blocks = div_up(n_nodes, rows_per_cta);
 #define RGNN_SPLIT_CASE(DE_)                                                                                   \
   case DE_:                                                                                                    \
-    edge_aggregate_split_kernel<MODE, DE_><<<blocks, kSplitThreads, 0, stream>>>(bm, bt, s.p, bias, w_e, ldwe, ea, csc_ptr, \
-                                                                                 csc_src, n, rows_per_cta, out_m, out_t, iso); \
+    if (threads == 512)                                                                                        \
+      edge_aggregate_split_kernel<MODE, DE_, 512><<<blocks, 512, 0, stream>>>(bm, bt, s.p, bias, w_e, ldwe, ea, csc_ptr, \
+                                                                              csc_src, n, rows_per_cta, out_m, out_t, iso); \
+    else                                                                                                       \
+      edge_aggregate_split_kernel<MODE, DE_, 384><<<blocks, 384, 0, stream>>>(bm, bt, s.p, bias, w_e, ldwe, ea, csc_ptr, \
+                                                                              csc_src, n, rows_per_cta, out_m, out_t, iso); \
     break;
   switch (s.de) {
     RGNN_SPLIT_CASE(1) RGNN_SPLIT_CASE(2) RGNN_SPLIT_CASE(3) RGNN_SPLIT_CASE(4)
