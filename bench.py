@@ -140,6 +140,11 @@ def cpu_sample(wl):
 
 def run_cpu_baseline(wl, steps: int, warmup: int):
     import torch
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm may use every host core it can
+    try:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+    except RuntimeError:
+        pass
     params = make_params(wl)
     sample = cpu_sample(wl)
     for _ in range(warmup):
