@@ -61,10 +61,13 @@ frame_bbox_kernel(const T* __restrict__ basis, int dims, int64_t n, const int64_
       mxy = fmax(mxy, __shfl_xor_sync(full, mxy, o));
     }
     if ((threadIdx.x & 31) == 0) {
-      atomicMin(&bbox[f0 * 4 + 0], double_to_ordered(mnx));
-      atomicMin(&bbox[f0 * 4 + 1], double_to_ordered(mny));
-      atomicMax(&bbox[f0 * 4 + 2], double_to_ordered(mxx));
-      atomicMax(&bbox[f0 * 4 + 3], double_to_ordered(mxy));
+      // skip the (same-address, serialised) atomics when the warp cannot move the box
+      const long long a = double_to_ordered(mnx), b = double_to_ordered(mny), c = double_to_ordered(mxx), d = double_to_ordered(mxy);
+      volatile long long* vb = bbox + f0 * 4;
+      if (a < vb[0]) atomicMin(&bbox[f0 * 4 + 0], a);
+      if (b < vb[1]) atomicMin(&bbox[f0 * 4 + 1], b);
+      if (c > vb[2]) atomicMax(&bbox[f0 * 4 + 2], c);
+      if (d > vb[3]) atomicMax(&bbox[f0 * 4 + 3], d);
     }
   } else if (valid) {
     atomicMin(&bbox[f * 4 + 0], double_to_ordered(x));

@@ -846,7 +846,12 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   }
 
   if (trace != nullptr && tid == 0) trace[3 * 64 + 1] = clock64();
-  if (timed_out && p.status != nullptr) atomicExch(p.status, RGNN_ERR_CUDA);
+  // a barrier that never completes is a kernel bug: fail loudly (sticky launch error at the caller's next
+  // synchronisation) instead of handing back a partly computed result
+  if (timed_out) {
+    if (p.status != nullptr) atomicExch(p.status, RGNN_ERR_CUDA);
+    __trap();
+  }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
