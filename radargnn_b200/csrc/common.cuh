@@ -158,8 +158,8 @@ size_t bn_scratch_doubles(int64_t n, int32_t c);
 int bn_statistics(const float* x, int64_t ldx, int64_t n, int32_t c, const float* weight, const float* bias,
                   float eps, float momentum, float* running_mean, float* running_var, float* mean,
                   float* scale, float* beta, double* scratch, cudaStream_t stream);
-// Same finalisation from column sums produced elsewhere (node_gemm epilogue): partial[(p*2)*c + ch] =
-// sum, partial[(p*2+1)*c + ch] = sum of squares of partition p.
+// Same finalisation from column sums produced elsewhere (node_gemm epilogue), channel-major:
+// partial[ch * P + p] = sum, partial[(c + ch) * P + p] = sum of squares of partition p of P.
 int bn_finalize_partials(const double* partial, int64_t n_partials, int64_t n, int32_t c, const float* weight,
                          const float* bias, float eps, float momentum, float* running_mean, float* running_var,
                          float* mean, float* scale, float* beta, cudaStream_t stream);

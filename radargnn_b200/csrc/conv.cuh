@@ -47,7 +47,7 @@ struct ConvWorkspace {
   float* wpack_pre;      // packed W_s image
   float* wpack_post;     // packed [W_x | W_m | W_fold] image
   float* w_fold;         // [c_out, c]
-  double* bn_partial;    // [tc_tiles(N)][2][c_out] column sums of the layer output
+  double* bn_partial;    // [2][c_out][tc_tiles(N)] column sums / squares of the layer output
   int32_t* tc_status;    // device flag
 };
 

@@ -61,13 +61,10 @@ frame_bbox_kernel(const T* __restrict__ basis, int dims, int64_t n, const int64_
       mxy = fmax(mxy, __shfl_xor_sync(full, mxy, o));
     }
     if ((threadIdx.x & 31) == 0) {
-      // skip the (same-address, serialised) atomics when the warp cannot move the box
-      const long long a = double_to_ordered(mnx), b = double_to_ordered(mny), c = double_to_ordered(mxx), d = double_to_ordered(mxy);
-      volatile long long* vb = bbox + f0 * 4;
-      if (a < vb[0]) atomicMin(&bbox[f0 * 4 + 0], a);
-      if (b < vb[1]) atomicMin(&bbox[f0 * 4 + 1], b);
-      if (c > vb[2]) atomicMax(&bbox[f0 * 4 + 2], c);
-      if (d > vb[3]) atomicMax(&bbox[f0 * 4 + 3], d);
+      atomicMin(&bbox[f0 * 4 + 0], double_to_ordered(mnx));
+      atomicMin(&bbox[f0 * 4 + 1], double_to_ordered(mny));
+      atomicMax(&bbox[f0 * 4 + 2], double_to_ordered(mxx));
+      atomicMax(&bbox[f0 * 4 + 3], double_to_ordered(mxy));
     }
   } else if (valid) {
     atomicMin(&bbox[f * 4 + 0], double_to_ordered(x));
@@ -165,6 +162,25 @@ cell_sort_kernel(const int32_t* __restrict__ cell_start, int total_cells, int32_
   int32_t* a = sorted_idx + cell_start[c];
   const int n = cell_start[c + 1] - cell_start[c];
   if (n < 2) return;
+  if (n <= 8) {
+    // the common case (~4 points per cell): registers + a fixed odd-even transposition network instead of a
+    // chain of dependent global loads and stores
+    int32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = j < n ? a[j] : 0x7fffffff;
+#pragma unroll
+    for (int round = 0; round < 8; ++round) {
+#pragma unroll
+      for (int j = round & 1; j + 1 < 8; j += 2) {
+        const int32_t lo = min(v[j], v[j + 1]), hi = max(v[j], v[j + 1]);
+        v[j] = lo; v[j + 1] = hi;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < n) a[j] = v[j];
+    return;
+  }
   if (n <= 32) {
     for (int j = 1; j < n; ++j) {
       const int32_t v = a[j];

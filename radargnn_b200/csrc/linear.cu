@@ -109,8 +109,8 @@ bn_partial_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int c, do
   if (threadIdx.y == 0 && ch < c) {
 #pragma unroll
     for (int g = 1; g < 8; ++g) { s += ssum[g][threadIdx.x]; q += ssq[g][threadIdx.x]; }
-    partial[(static_cast<int64_t>(blockIdx.x) * 2) * c + ch] = s;
-    partial[(static_cast<int64_t>(blockIdx.x) * 2 + 1) * c + ch] = q;
+    partial[static_cast<int64_t>(ch) * gridDim.x + blockIdx.x] = s;          // channel-major, see bn_finalize_kernel
+    partial[static_cast<int64_t>(c + ch) * gridDim.x + blockIdx.x] = q;
   }
 }
 
@@ -124,8 +124,8 @@ bn_finalize_kernel(const double* __restrict__ partial, int n_partials, int64_t n
   const int ch = blockIdx.x;
   double s = 0.0, q = 0.0;
   for (int p = threadIdx.x; p < n_partials; p += 128) {
-    s += partial[(static_cast<int64_t>(p) * 2) * c + ch];
-    q += partial[(static_cast<int64_t>(p) * 2 + 1) * c + ch];
+    s += partial[static_cast<int64_t>(ch) * n_partials + p];          // contiguous over p: coalesced
+    q += partial[static_cast<int64_t>(c + ch) * n_partials + p];
   }
   ss[threadIdx.x] = s;
   sq[threadIdx.x] = q;

@@ -838,8 +838,10 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
                              (static_cast<double>(cs[2 * np + c]) + static_cast<double>(cs[3 * np + c]));
           const double sq2 = (static_cast<double>(cq[c]) + static_cast<double>(cq[np + c])) +
                              (static_cast<double>(cq[2 * np + c]) + static_cast<double>(cq[3 * np + c]));
-          p.bn_partial[(tile * 2) * p.n + c] = sum;
-          p.bn_partial[(tile * 2 + 1) * p.n + c] = sq2;
+          // channel-major: partial[ch * T + tile] (sums), partial[(n + ch) * T + tile] (squares), so that the
+          // finalisation reads every channel's partials contiguously
+          p.bn_partial[static_cast<int64_t>(c) * n_tiles + tile] = sum;
+          p.bn_partial[static_cast<int64_t>(p.n + c) * n_tiles + tile] = sq2;
         }
       }
     }

@@ -51,7 +51,7 @@ struct TcGemmParams {
   int32_t res_relu = 0;
   float* y = nullptr; int64_t ldy = 0; int32_t n_store = 0;      // columns written (>= n; extras are zeros)
   float* y2 = nullptr; int64_t ldy2 = 0; int32_t n_split = 0;    // optional: columns >= n_split go to y2[:, col - n_split]
-  double* bn_partial = nullptr;                                  // [tc_tiles(m)][2][n] column sums / squares
+  double* bn_partial = nullptr;                                  // [2][n][tc_tiles(m)] column sums / squares per tile
   int64_t m = 0;
   int32_t* status = nullptr;                                     // device flag set if a barrier wait timed out
   long long* trace = nullptr;                                    // debug timeline of CTA 0 (node_gemm.cu)
