@@ -477,3 +477,80 @@ def test_tensor_core_path_isolated_nodes_and_weight_cache(ops):
     got2 = ops.conv_forward(cp, x.to(DEV), csc, ea.to(DEV)).cpu()
     want2 = mo.mpnn_conv_forward(params, x, ei, ea, "max", dtype=torch.float64)
     assert mo.relative_error(got2, want2) <= 2e-5
+
+
+def test_pipeline_split_layout_radius_isolated_nodes_and_frames(ops):
+    """C = 64 MPNNConv (split message layout, TMA / bulk-copy contractions) on a radius graph over batched
+    radar frames: many nodes without incoming edge, in-degrees from 0 to far above 32, a one-point frame."""
+    frames = [synthetic.radar_frame(n, seed=40 + s) for s, n in enumerate([280, 1, 330, 150])]
+    Xs = [f.X_cc.copy() for f in frames]
+    Vs = [f.V_cc_compensated.copy() for f in frames]
+    blob = np.random.default_rng(7)                    # a dense blob: in-degrees of ~60 inside frame 0
+    Xs[0] = np.concatenate([Xs[0], np.array([40.0, 10.0]) + 0.5 * blob.standard_normal((60, 2))])
+    Vs[0] = np.concatenate([Vs[0], blob.standard_normal((60, 2))])
+    X, V = np.concatenate(Xs), np.concatenate(Vs)
+    ptr = np.zeros(len(Xs) + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum([x.shape[0] for x in Xs])
+    n = X.shape[0]
+    feats = ["relative_position"]
+    params = _stack_params(2, 64, 64, 2, "MPNNConv", seed=9)
+    x0 = synthetic.node_embeddings(n, 64, seed=2)
+    for aggr in ("max", "mean"):
+        cfg = _pipeline_cfg(ops, params, 2, "MPNNConv", aggr, algorithm="radius", k=6, r=2.0, distance_definition="X",
+                            edge_features=feats, edge_mode="directed")
+        ei, ea, h = ops.pipeline_forward(cfg, _dev(X, torch.float32), _dev(V, torch.float32), _dev(x0), ptr)
+        E = go.batched_edges(Xs, "radius", k=6, r=2.0)
+        np.testing.assert_array_equal(ei.cpu().numpy().T, E)
+        indeg = np.bincount(E[:, 1], minlength=n)
+        assert (indeg == 0).any() and indeg.max() > 32
+        ef = go.edge_features(X, V, E, feats, "directed").astype(np.float32)
+        want = mo.conv_stack_forward(params, torch.from_numpy(x0), torch.from_numpy(E.T.copy()), torch.from_numpy(ef),
+                                     2, "MPNNConv", aggr, dtype=torch.float64)
+        assert mo.relative_error(h.cpu(), want) <= 1e-4
+
+
+def test_host_entry_point_replays_its_graph(ops):
+    """rgnn_pipeline_forward_host captures its work into a CUDA graph and replays it while the arguments stay
+    the same: a replay must read the buffers' current contents, and changed frame offsets must re-capture."""
+    import ctypes as C
+    from radargnn_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device(DEV)
+    fr = synthetic.uniform_square(3000, seed=4)
+    params = _stack_params(2, 64, 64, 2, "MPNNConv", seed=5)
+    cfg = _pipeline_cfg(ops, params, 2, "MPNNConv", "max", algorithm="knn", k=8, edge_features=["relative_position"])
+    handle = ops._PipelineHandle(cfg)
+    n = 3000
+    pos_h = torch.from_numpy(fr.X_cc.astype(np.float32)).pin_memory()
+    vel_h = torch.from_numpy(fr.V_cc_compensated.astype(np.float32)).pin_memory()
+    x0_h = torch.from_numpy(synthetic.node_embeddings(n, 64, seed=6)).pin_memory()
+    h_h = torch.empty((n, 64), dtype=torch.float32).pin_memory()
+    sp = torch.cuda.current_stream().cuda_stream
+
+    one = np.array([0, n], dtype=np.int64)
+    two = np.array([0, 1200, n], dtype=np.int64)    # other frame offsets: another graph
+    need = max(lib.rgnn_pipeline_host_workspace_bytes(C.byref(handle.desc), n, len(p) - 1, ops.knn_edge_count(p, 8), 64)
+               for p in (one, two))
+    ws = _lib.workspace(need, dev)                  # kept alive: its pointer is part of the replay key
+
+    def rerun(ptr):
+        n_edges = ops.knn_edge_count(ptr, 8)
+        _lib.check(lib.rgnn_pipeline_forward_host(C.byref(handle.desc), pos_h.data_ptr(), vel_h.data_ptr(), x0_h.data_ptr(), 64,
+                                                  ptr.ctypes.data, len(ptr) - 1, None, n_edges, None, h_h.data_ptr(),
+                                                  ws.data_ptr(), ws.numel(), sp))
+        return h_h.clone()
+
+    def device_path(ptr):
+        _, _, h = ops.pipeline_forward(cfg, pos_h.to(dev), vel_h.to(dev), x0_h.to(dev), ptr)
+        return h.cpu()
+
+    a = rerun(one)                                  # first call: capture + launch
+    torch.testing.assert_close(a, device_path(one), rtol=0, atol=0)
+    b = rerun(one)
+    torch.testing.assert_close(b, a, rtol=0, atol=0)
+    x0_h.mul_(0.5).add_(0.25)                       # new contents, same pointers: the replay must see them
+    c = rerun(one)
+    torch.testing.assert_close(c, device_path(one), rtol=0, atol=0)
+    assert not torch.equal(c, a)
+    d = rerun(two)
+    torch.testing.assert_close(d, device_path(two), rtol=0, atol=0)
