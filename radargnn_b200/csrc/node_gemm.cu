@@ -1,6 +1,6 @@
 // node_gemm.cu -- the dense node-level contractions on the 5th-generation tensor cores.
 //
-//   y[m, n] = in(A)[m, K] . W[n, K]^T + bias (+ residual)        A = [a1 | a2 | rowscale * a1]
+//   y[m, n] = in(A)[m, K] . W[n, K]^T + bias (+ residual)        A = [a1 | a2 | a_tail | rowscale * a1]
 //
 // used for B = x W_s^T (first message Linear, source half) and for the node update
 // post_mlp([x ; M]) of MPNNConv / RadarPointGNNConv (reference gnn/mpnn_layers.py:89-90, 98-99,
@@ -8,18 +8,18 @@
 //   * tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = padded output width, accumulator in TMEM;
 //   * 3xTF32: every fp32 operand is split into hi (top 19 bits) + lo (remainder) and the product is
 //     accumulated as hi*hi + lo*hi + hi*lo in fp32 -- ~2^-21 relative per product, i.e. fp32-grade
-//     results (plain TF32 is ~1e-3 and would miss the reference's 1e-4 parity bar);
-//   * the A operand is produced by the CTA itself (BatchNorm+ReLU of the previous layer applied on
-//     load, hi/lo split), so it is written to shared memory by the threads themselves, in the K-major
-//     128-byte-swizzle layout TMA would produce (full-rate operand fetch; the no-swizzle core-matrix
-//     layout measured 4x slower MMAs), instead of by TMA: raw 32-float K chunks
-//     stream global -> shared through a 3-deep cp.async ring (the stream runs ahead across tiles, so
-//     loads stay in flight during the epilogue), each thread converts the items it loaded itself and
-//     the MMAs of chunk c drain while chunk c+1 is converted;
-//   * W (hi and lo images, packed once per call by pack_weights_kernel) stays resident in shared
+//     results (plain TF32 is ~1e-3 and would miss the reference's 1e-4 parity bar); for narrow outputs
+//     hi*hi and hi*lo are one MMA with N = 2 np against [W_hi ; W_lo];
+//   * the A operand needs a transform (BatchNorm+ReLU of the previous layer applied on load, hi/lo split),
+//     so it cannot go from TMA straight to the MMA: raw fp32 panels (128 rows x 32 floats) are brought
+//     into a shared-memory ring by the async engines (TMA tensor maps for row-major operands, bulk copies
+//     for the panel-major M', 16-byte cp.async for a gathered operand), converter warps transform / split
+//     them and write the hi and lo images into TENSOR MEMORY (tcgen05.st), and the MMAs read A from TMEM;
+//   * W (hi and lo images, packed per weight version by pack_weights_kernel) stays resident in shared
 //     memory for all tiles of the CTA;
-//   * epilogue: tcgen05.ld (32 lanes x 16 columns per warp) -> bias / residual -> per-warp staging ->
-//     coalesced stores, plus deterministic per-tile column sums for the BatchNorm statistics.
+//   * epilogue: tcgen05.ld (32 columns per warp) -> per-warp transpose buffer -> coalesced 128-byte row
+//     stores with bias / residual, plus deterministic per-tile column sums for the BatchNorm statistics.
+// DESIGN.md sections 3.5 / 3.6 hold the measurements behind every one of these choices.
 #include <string.h>
 
 #include "node_gemm.cuh"
