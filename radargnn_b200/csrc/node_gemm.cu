@@ -993,7 +993,15 @@ int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
   p.raw_slots = pick_raw_slots(p.np, p.kp, p.staged_epilogue);
   if (p.raw_slots < 2 || p.a_stages < 1) return RGNN_ERR_UNSUPPORTED;
   // converter groups: ring slots and TMEM stages in multiples of the group count (see the converter role)
-  p.conv_groups = (p.raw_slots >= 3 && p.a_stages >= 3) ? 3 : ((p.raw_slots >= 2 && p.a_stages >= 2) ? 2 : 1);
+  // Three groups when the ring and TMEM allow it (RGNN_GEMM_GROUPS forces 1 / 2 / 3 for experiments: two
+  // groups over four ring slots instead of three over three measured the same on the update contraction).
+  {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("RGNN_GEMM_GROUPS"); forced = e != nullptr ? atoi(e) : 0; }
+    int groups = (p.raw_slots >= 3 && p.a_stages >= 3) ? 3 : ((p.raw_slots >= 2 && p.a_stages >= 2) ? 2 : 1);
+    if (forced >= 1 && forced <= groups) groups = forced;
+    p.conv_groups = groups;
+  }
   p.raw_slots = p.raw_slots / p.conv_groups * p.conv_groups;
   p.a_stages = p.a_stages / p.conv_groups * p.conv_groups;
   if (p.y2 != nullptr && (!p.staged_epilogue || (p.n_split & 3) != 0 || (p.ldy2 & 3) != 0)) return RGNN_ERR_UNSUPPORTED;
