@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RGNN_ABI_VERSION 1
+#define RGNN_ABI_VERSION 2
 
 typedef void* rgnn_stream_t; /* cudaStream_t */
 
@@ -42,7 +42,9 @@ typedef enum rgnn_status {
   RGNN_ERR_DOT_PRODUCT = 5,     /* graph_constructor/features.py:56 "Error in dot product calculation" */
   RGNN_ERR_INVALID_FEATURE = 6, /* graph_constructor/graph.py:220 "Invalid feature specified" */
   RGNN_ERR_UNSUPPORTED = 7,
-  RGNN_ERR_NO_DEVICE = 8
+  RGNN_ERR_NO_DEVICE = 8,
+  RGNN_ERR_NON_FINITE_INPUT = 9,   /* sklearn check_array: ValueError "Input contains NaN" / "infinity" */
+  RGNN_ERR_INDEX_OUT_OF_RANGE = 10 /* edge_index entry outside [0, N): PyG's gather raises an index error */
 } rgnn_status;
 
 typedef enum rgnn_dtype { RGNN_F32 = 0, RGNN_F64 = 1 } rgnn_dtype;
@@ -113,10 +115,13 @@ int64_t rgnn_knn_edge_count(const int64_t* frame_ptr_host, int32_t n_frames, int
 
 /* k-NN graph (graph.py:52-66).  Row i*k..i*k+k-1 (per frame) lists the k nearest
  * neighbours of point i by ascending (fp64 squared distance, index); self excluded by
- * index; frames with n_f <= 1 emit nothing (graph.py:45). */
+ * index; frames with n_f <= 1 emit nothing (graph.py:45).
+ * *error_flag (device int32, may be NULL; zeroed by the call) becomes RGNN_ERR_NON_FINITE_INPUT when a
+ * coordinate is NaN or infinite (sklearn's check_array raises "Input contains NaN"); the rows of such
+ * points are then meaningless.  The radius count call reports the same condition as its return value. */
 int rgnn_graph_build_knn(const void* basis, int32_t basis_dtype, int32_t dims,
                          const int64_t* frame_ptr_host, int32_t n_frames, int32_t k,
-                         int64_t* edge_index, int64_t n_edges,
+                         int64_t* edge_index, int64_t n_edges, int32_t* error_flag,
                          void* workspace, size_t workspace_bytes, rgnn_stream_t stream);
 
 /* Radius graph (graph.py:68-82), two calls sharing the workspace:
@@ -174,8 +179,11 @@ int rgnn_node_features(const double* rcs, const double* time_index, const int32_
  * node (csc_src) and the position of that edge in edge_index / edge_attr (csc_eid).
  * Messages are reduced at edge_index[1] (flow = source_to_target). */
 size_t rgnn_csc_workspace_bytes(int64_t n_nodes, int64_t n_edges);
+/* *error_flag (device int32, may be NULL; zeroed by the call) becomes RGNN_ERR_INDEX_OUT_OF_RANGE when
+ * edge_index holds an id outside [0, n_nodes) -- PyG's gather raises an index error there; such edges
+ * are left out of the view instead of being used as addresses. */
 int rgnn_csc_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes,
-                   int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid,
+                   int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid, int32_t* error_flag,
                    void* workspace, size_t workspace_bytes, rgnn_stream_t stream);
 
 /* One graph-convolution layer.  Weights are PyG `Linear` parameters: [out, in] row-major

@@ -17,7 +17,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "librgnn_b200.so")
 
 # ---- enums of include/rgnn.h -------------------------------------------------------------
 OK, ERR_INVALID_ARGUMENT, ERR_K_NOT_SMALLER_THAN_N, ERR_WORKSPACE_TOO_SMALL, ERR_CUDA, \
-    ERR_DOT_PRODUCT, ERR_INVALID_FEATURE, ERR_UNSUPPORTED, ERR_NO_DEVICE = range(9)
+    ERR_DOT_PRODUCT, ERR_INVALID_FEATURE, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_NON_FINITE_INPUT, \
+    ERR_INDEX_OUT_OF_RANGE = range(11)
+ABI_VERSION = 2
 F32, F64 = 0, 1
 DIRECTED, UNDIRECTED = 0, 1
 EDGE_FEATURES = {
@@ -80,7 +82,7 @@ _PROTOTYPES = {
     "rgnn_graph_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "rgnn_knn_edge_count": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int)]),
     "rgnn_graph_build_knn": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
-                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rgnn_graph_build_radius_count": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                                 C.c_double, C.POINTER(C.c_int64), C.c_void_p, C.c_size_t,
                                                 C.c_void_p]),
@@ -97,7 +99,7 @@ _PROTOTYPES = {
                                      C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "rgnn_csc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "rgnn_csc_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_size_t, C.c_void_p]),
+                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rgnn_conv_packed_bytes": (C.c_size_t, [C.POINTER(ConvDesc)]),
     "rgnn_conv_pack_weights": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     "rgnn_conv_workspace_bytes": (C.c_size_t, [C.POINTER(ConvDesc), C.c_int64, C.c_int64]),
@@ -142,7 +144,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.rgnn_abi_version() != 1:
+    if lib.rgnn_abi_version() != ABI_VERSION:
         raise ImportError("librgnn_b200.so ABI version mismatch: rebuild the library")
     _lib = lib
     return lib
@@ -159,8 +161,10 @@ def check(status: int) -> None:
         return
     lib = load()
     msg = lib.rgnn_status_string(status).decode()
-    if status == ERR_K_NOT_SMALLER_THAN_N:
-        raise ValueError(msg)  # sklearn's ValueError through graph.py:57
+    if status in (ERR_K_NOT_SMALLER_THAN_N, ERR_NON_FINITE_INPUT):
+        raise ValueError(msg)  # sklearn's ValueError through graph.py:57 (n_neighbors / check_array)
+    if status == ERR_INDEX_OUT_OF_RANGE:
+        raise IndexError(msg)  # PyG: index_select on edge_index raises an index error
     if status in (ERR_DOT_PRODUCT, ERR_INVALID_FEATURE):
         raise Exception(msg)  # features.py:56, graph.py:220
     if status == ERR_CUDA:

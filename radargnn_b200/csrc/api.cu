@@ -63,6 +63,8 @@ const char* rgnn_status_string(int status) {
     case RGNN_ERR_INVALID_FEATURE: return "Invalid feature specified";
     case RGNN_ERR_UNSUPPORTED: return "unsupported configuration";
     case RGNN_ERR_NO_DEVICE: return "no CUDA device";
+    case RGNN_ERR_NON_FINITE_INPUT: return "Input contains NaN or infinity";
+    case RGNN_ERR_INDEX_OUT_OF_RANGE: return "edge_index holds a node id outside [0, N)";
     default: return "unknown status";
   }
 }

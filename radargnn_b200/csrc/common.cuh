@@ -94,15 +94,35 @@ struct SizeArena {
   }
 };
 
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs)
+inline int current_device_index() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+  return dev;
+}
+constexpr int kMaxDevices = 64;
 inline int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-    if (cached <= 0) cached = 148;
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device_index();
+  int& c = cached[dev < kMaxDevices ? dev : 0];
+  if (c == 0 || dev >= kMaxDevices) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    if (dev >= kMaxDevices) return v;
+    c = v;
   }
-  return cached;
+  return c;
+}
+
+// One-time per-device opt-in to more than 48 KB of dynamic shared memory (cudaFuncSetAttribute applies to
+// the current device only, so a process-wide flag would leave a second GPU unconfigured).
+template <typename KernelT>
+inline cudaError_t opt_in_dynamic_smem(KernelT kernel, bool (&done)[kMaxDevices], int bytes) {
+  const int dev = current_device_index();
+  if (dev < kMaxDevices && done[dev]) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev < kMaxDevices) done[dev] = true;
+  return e;
 }
 
 inline unsigned div_up(int64_t a, int64_t b) { return static_cast<unsigned>((a + b - 1) / b); }

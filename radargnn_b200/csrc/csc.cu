@@ -10,20 +10,33 @@
 namespace rgnn {
 namespace {
 
-__global__ void __launch_bounds__(256)
-count_targets_kernel(const int64_t* __restrict__ dst, int64_t n_edges, int32_t* __restrict__ count,
-                     const int32_t* __restrict__ node_map) {
-  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (e < n_edges) atomicAdd(&count[node_map != nullptr ? node_map[dst[e]] : dst[e]], 1);
+// An edge whose source or target id lies outside [0, n_nodes) must never be used as an address (PyG's
+// gather raises an index error): it is left out of the view and reported through *error_flag.
+__device__ __forceinline__ bool edge_in_range(int64_t s, int64_t t, int64_t n_nodes) {
+  return static_cast<uint64_t>(s) < static_cast<uint64_t>(n_nodes) && static_cast<uint64_t>(t) < static_cast<uint64_t>(n_nodes);
 }
 
 __global__ void __launch_bounds__(256)
-fill_slots_kernel(const int64_t* __restrict__ edge_index, int64_t n_edges, const int32_t* __restrict__ csc_ptr,
+count_targets_kernel(const int64_t* __restrict__ edge_index, int64_t n_edges, int64_t n_nodes,
+                     int32_t* __restrict__ count, const int32_t* __restrict__ node_map, int32_t* __restrict__ error_flag) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int64_t s = edge_index[e], t = edge_index[n_edges + e];
+  if (!edge_in_range(s, t, n_nodes)) {
+    if (error_flag != nullptr) atomicExch(error_flag, RGNN_ERR_INDEX_OUT_OF_RANGE);
+    return;
+  }
+  atomicAdd(&count[node_map != nullptr ? node_map[t] : t], 1);
+}
+
+__global__ void __launch_bounds__(256)
+fill_slots_kernel(const int64_t* __restrict__ edge_index, int64_t n_edges, int64_t n_nodes, const int32_t* __restrict__ csc_ptr,
                   int32_t* __restrict__ cursor, int32_t* __restrict__ csc_src, int32_t* __restrict__ csc_eid,
                   const int32_t* __restrict__ node_map) {
   const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
   int64_t t = edge_index[n_edges + e], s = edge_index[e];
+  if (!edge_in_range(s, t, n_nodes)) return;   // counted out (and flagged) by count_targets_kernel
   if (node_map != nullptr) { t = node_map[t]; s = node_map[s]; }
   const int pos = csc_ptr[t] + atomicAdd(&cursor[t], 1);
   csc_eid[pos] = static_cast<int32_t>(e);
@@ -31,12 +44,13 @@ fill_slots_kernel(const int64_t* __restrict__ edge_index, int64_t n_edges, const
 }
 
 __global__ void __launch_bounds__(256)
-fill_slots_features_kernel(const int64_t* __restrict__ edge_index, int64_t n_edges, const int32_t* __restrict__ csc_ptr,
+fill_slots_features_kernel(const int64_t* __restrict__ edge_index, int64_t n_edges, int64_t n_nodes, const int32_t* __restrict__ csc_ptr,
                            int32_t* __restrict__ cursor, int32_t* __restrict__ csc_src, int32_t* __restrict__ csc_eid,
                            const int32_t* __restrict__ node_map, FusedEdgeAttr f) {
   const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
   const int64_t i = edge_index[e], j = edge_index[n_edges + e];
+  if (!edge_in_range(i, j, n_nodes)) return;
   int64_t t = j, s = i;
   if (node_map != nullptr) { t = node_map[t]; s = node_map[s]; }
   const int slot = csc_ptr[t] + atomicAdd(&cursor[t], 1);
@@ -90,19 +104,19 @@ sort_segments_kernel(const int32_t* __restrict__ csc_ptr, int64_t n_nodes, int32
 
 int csc_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, bool counts_ready,
               bool ordered, const CscWorkspace& w, int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid,
-              cudaStream_t stream, const int32_t* node_map) {
+              cudaStream_t stream, const int32_t* node_map, int32_t* error_flag) {
   RGNN_PROFILE("csc_build", stream);
   if (!counts_ready) {
     RGNN_CUDA_CHECK(cudaMemsetAsync(w.count, 0, sizeof(int32_t) * (n_nodes + 1), stream));
     if (n_edges > 0) {
-      count_targets_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index + n_edges, n_edges, w.count, node_map);
+      count_targets_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index, n_edges, n_nodes, w.count, node_map, error_flag);
       RGNN_LAUNCH_CHECK();
     }
   }
   RGNN_RETURN_IF_ERROR(exclusive_scan_i32(w.count, csc_ptr, n_nodes, w.scan_scratch, stream));
   if (n_edges == 0) return RGNN_OK;
   RGNN_CUDA_CHECK(cudaMemsetAsync(w.cursor, 0, sizeof(int32_t) * (n_nodes + 1), stream));
-  fill_slots_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index, n_edges, csc_ptr, w.cursor, csc_src, csc_eid, node_map);
+  fill_slots_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index, n_edges, n_nodes, csc_ptr, w.cursor, csc_src, csc_eid, node_map);
   RGNN_LAUNCH_CHECK();
   if (ordered) {
     sort_segments_kernel<<<div_up(n_nodes, 128), 128, 0, stream>>>(csc_ptr, n_nodes, csc_src, csc_eid);
@@ -131,6 +145,7 @@ fill_slots_features_knn_kernel(const int64_t* __restrict__ edge_index, int64_t n
   const int64_t i = sorted_idx[qs];
   const int64_t e = g.edge_off + (i - g.pt_begin) * k + jj;
   const int64_t j = edge_index[n_edges + e];
+  if (static_cast<uint64_t>(j) >= static_cast<uint64_t>(n_points)) return;   // sentinel of a non-finite query (flagged by the search)
   const int t = rank[j];   // the one scattered lookup left: neighbour id -> sorted position
   const int slot = csc_ptr[t] + atomicAdd(&cursor[t], 1);
   csc_eid[slot] = static_cast<int32_t>(e);
@@ -190,17 +205,18 @@ int csc_build_fused(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes,
                     const CscWorkspace& w, int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid, cudaStream_t stream,
                     const int32_t* node_map, const FusedEdgeAttr& fea) {
   RGNN_PROFILE("csc_build_edge_attr", stream);
+  int32_t* error_flag = fea.error_flag;
   if (!counts_ready) {
     RGNN_CUDA_CHECK(cudaMemsetAsync(w.count, 0, sizeof(int32_t) * (n_nodes + 1), stream));
     if (n_edges > 0) {
-      count_targets_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index + n_edges, n_edges, w.count, node_map);
+      count_targets_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index, n_edges, n_nodes, w.count, node_map, error_flag);
       RGNN_LAUNCH_CHECK();
     }
   }
   RGNN_RETURN_IF_ERROR(exclusive_scan_i32(w.count, csc_ptr, n_nodes, w.scan_scratch, stream));
   if (n_edges == 0) return RGNN_OK;
   RGNN_CUDA_CHECK(cudaMemsetAsync(w.cursor, 0, sizeof(int32_t) * (n_nodes + 1), stream));
-  fill_slots_features_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index, n_edges, csc_ptr, w.cursor, csc_src,
+  fill_slots_features_kernel<<<div_up(n_edges, 256), 256, 0, stream>>>(edge_index, n_edges, n_nodes, csc_ptr, w.cursor, csc_src,
                                                                       csc_eid, node_map, fea);
   RGNN_LAUNCH_CHECK();
   return RGNN_OK;
@@ -221,7 +237,7 @@ size_t rgnn_csc_workspace_bytes(int64_t n_nodes, int64_t n_edges) {
 }
 
 int rgnn_csc_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int32_t* csc_ptr,
-                   int32_t* csc_src, int32_t* csc_eid, void* workspace, size_t workspace_bytes,
+                   int32_t* csc_src, int32_t* csc_eid, int32_t* error_flag, void* workspace, size_t workspace_bytes,
                    rgnn_stream_t stream) {
   if (n_nodes < 0 || n_edges < 0 || n_edges > 0x7ffffff0LL || n_nodes > 0x7ffffff0LL) return RGNN_ERR_INVALID_ARGUMENT;
   if (csc_ptr == nullptr || (n_edges > 0 && (edge_index == nullptr || csc_src == nullptr || csc_eid == nullptr)))
@@ -230,8 +246,9 @@ int rgnn_csc_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, 
   Arena arena(workspace, workspace_bytes);
   CscWorkspace w = carve_csc_workspace(arena, n_nodes);
   if (arena.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+  if (error_flag != nullptr) RGNN_CUDA_CHECK(cudaMemsetAsync(error_flag, 0, sizeof(int32_t), static_cast<cudaStream_t>(stream)));
   return csc_build(edge_index, n_edges, n_nodes, false, true, w, csc_ptr, csc_src, csc_eid,
-                   static_cast<cudaStream_t>(stream));
+                   static_cast<cudaStream_t>(stream), nullptr, error_flag);
 }
 
 }  // extern "C"

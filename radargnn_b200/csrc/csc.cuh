@@ -28,7 +28,7 @@ inline CscWorkspace carve_csc_workspace(ArenaT& a, int64_t n_nodes) {
 // cell-sorted node order); csc_eid always refers to the caller's edge order.
 int csc_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, bool counts_ready, bool ordered,
               const CscWorkspace& w, int32_t* csc_ptr, int32_t* csc_src, int32_t* csc_eid, cudaStream_t stream,
-              const int32_t* node_map = nullptr);
+              const int32_t* node_map = nullptr, int32_t* error_flag = nullptr);
 
 // Fused variant for the pipeline (unordered segments only): the slot-fill pass also computes the edge
 // attributes (fp64 arithmetic, f32 output) and writes them twice -- edge_attr [E, De] in the caller's

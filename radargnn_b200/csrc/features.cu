@@ -16,11 +16,15 @@ namespace {
 template <typename T, typename OT>
 __global__ void __launch_bounds__(256)
 edge_features_kernel(const T* __restrict__ pos, const T* __restrict__ vel, int pos_dims, int vel_dims,
-                     const int64_t* __restrict__ edge_index, int64_t n_edges, EdgeFeatureSpec spec,
+                     const int64_t* __restrict__ edge_index, int64_t n_edges, int64_t n_points, EdgeFeatureSpec spec,
                      OT* __restrict__ out, int32_t* __restrict__ error_flag) {
   const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
   const int64_t i = edge_index[e], j = edge_index[n_edges + e];
+  if (static_cast<uint64_t>(i) >= static_cast<uint64_t>(n_points) || static_cast<uint64_t>(j) >= static_cast<uint64_t>(n_points)) {
+    atomicExch(error_flag, RGNN_ERR_INDEX_OUT_OF_RANGE);   // never used as an address
+    return;
+  }
   double xi[4], xj[4], vi[4], vj[4];
   efm::load_vec(pos, i, pos_dims, xi);
   efm::load_vec(pos, j, pos_dims, xj);
@@ -118,15 +122,14 @@ int make_edge_feature_spec(const int32_t* features_host, int32_t n_features, int
 }
 
 int launch_edge_features(const void* pos, const void* vel, int32_t in_dtype, int32_t pos_dims, int32_t vel_dims,
-                         const int64_t* edge_index, int64_t n_edges, const EdgeFeatureSpec& spec,
+                         const int64_t* edge_index, int64_t n_edges, int64_t n_points, const EdgeFeatureSpec& spec,
                          void* edge_attr, int32_t out_dtype, int32_t* error_flag, cudaStream_t stream) {
-  RGNN_CUDA_CHECK(cudaMemsetAsync(error_flag, 0, sizeof(int32_t), stream));
   if (n_edges == 0 || spec.width == 0) return RGNN_OK;
   RGNN_PROFILE("edge_features", stream);
   const unsigned blocks = div_up(n_edges, 256);
 #define RGNN_EF_LAUNCH(T, OT)                                                                          \
   edge_features_kernel<T, OT><<<blocks, 256, 0, stream>>>(static_cast<const T*>(pos),                  \
-      static_cast<const T*>(vel), pos_dims, vel_dims, edge_index, n_edges, spec,                       \
+      static_cast<const T*>(vel), pos_dims, vel_dims, edge_index, n_edges, n_points, spec,             \
       static_cast<OT*>(edge_attr), error_flag)
   if (in_dtype == RGNN_F32 && out_dtype == RGNN_F32) RGNN_EF_LAUNCH(float, float);
   else if (in_dtype == RGNN_F32) RGNN_EF_LAUNCH(float, double);
@@ -161,7 +164,8 @@ int rgnn_edge_features(const void* pos, const void* vel, int32_t in_dtype, int32
   if (n_edges < 0 || n_points < 0 || error_flag == nullptr) return RGNN_ERR_INVALID_ARGUMENT;
   if (n_edges > 0 && (pos == nullptr || vel == nullptr || edge_index == nullptr || edge_attr == nullptr))
     return RGNN_ERR_INVALID_ARGUMENT;
-  return launch_edge_features(pos, vel, in_dtype, pos_dims, vel_dims, edge_index, n_edges, spec, edge_attr,
+  RGNN_CUDA_CHECK(cudaMemsetAsync(error_flag, 0, sizeof(int32_t), static_cast<cudaStream_t>(stream)));
+  return launch_edge_features(pos, vel, in_dtype, pos_dims, vel_dims, edge_index, n_edges, n_points, spec, edge_attr,
                               out_dtype, error_flag, static_cast<cudaStream_t>(stream));
 }
 

@@ -38,21 +38,35 @@ __device__ __forceinline__ int find_frame(const int64_t* __restrict__ frame_ptr,
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 frame_bbox_kernel(const T* __restrict__ basis, int dims, int64_t n, const int64_t* __restrict__ frame_ptr,
-                  int n_frames, long long* __restrict__ bbox) {
+                  int n_frames, long long* __restrict__ bbox, int32_t* __restrict__ status) {
+  // warp -> block reduction: a warp whose lanes lie in one frame reduces with shuffles, and when all warps
+  // of the block lie in the same frame the block issues ONE set of atomics (a single large frame would
+  // otherwise serialise thousands of warps on four addresses)
+  __shared__ double red[kThreads / 32][4];
+  __shared__ int red_frame[kThreads / 32];   // frame of a frame-uniform warp, -1 otherwise
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool valid = i < n;
   int f = -1;
   double x = 0.0, y = 0.0;
+  bool finite = true;
   if (valid) {
     f = n_frames == 1 ? 0 : find_frame(frame_ptr, n_frames, i);
     x = static_cast<double>(basis[i * dims]);
     y = static_cast<double>(basis[i * dims + 1]);
+    finite = isfinite(x) && isfinite(y);
+    for (int d = 2; d < dims; ++d) finite = finite && isfinite(static_cast<double>(basis[i * dims + d]));
+    // sklearn's check_array rejects such input ("Input contains NaN" / "infinity"): flag it and keep the
+    // point out of the bounding box so that the grid stays sane
+    if (!finite && status != nullptr) atomicExch(status, RGNN_ERR_NON_FINITE_INPUT);
   }
   const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int f0 = __shfl_sync(full, f, 0);
-  const bool uniform = __all_sync(full, f == f0) && f0 >= 0;
+  // lanes beyond n (last warp only) take part as neutral elements of frame f0
+  const bool uniform = f0 >= 0 && __all_sync(full, f == f0 || !valid);
+  double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
   if (uniform) {
-    double mnx = x, mny = y, mxx = x, mxy = y;
+    if (valid && finite) { mnx = x; mny = y; mxx = x; mxy = y; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       mnx = fmin(mnx, __shfl_xor_sync(full, mnx, o));
@@ -60,23 +74,58 @@ frame_bbox_kernel(const T* __restrict__ basis, int dims, int64_t n, const int64_
       mxx = fmax(mxx, __shfl_xor_sync(full, mxx, o));
       mxy = fmax(mxy, __shfl_xor_sync(full, mxy, o));
     }
-    if ((threadIdx.x & 31) == 0) {
-      atomicMin(&bbox[f0 * 4 + 0], double_to_ordered(mnx));
-      atomicMin(&bbox[f0 * 4 + 1], double_to_ordered(mny));
-      atomicMax(&bbox[f0 * 4 + 2], double_to_ordered(mxx));
-      atomicMax(&bbox[f0 * 4 + 3], double_to_ordered(mxy));
-    }
-  } else if (valid) {
+  } else if (valid && finite) {
     atomicMin(&bbox[f * 4 + 0], double_to_ordered(x));
     atomicMin(&bbox[f * 4 + 1], double_to_ordered(y));
     atomicMax(&bbox[f * 4 + 2], double_to_ordered(x));
     atomicMax(&bbox[f * 4 + 3], double_to_ordered(y));
   }
+  if (lane == 0) {
+    red[wid][0] = mnx; red[wid][1] = mny; red[wid][2] = mxx; red[wid][3] = mxy;
+    red_frame[wid] = uniform ? f0 : -1;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  constexpr int kWarps = kThreads / 32;
+  int w = 0;
+  while (w < kWarps) {   // runs of warps of the same frame -> one set of atomics per run
+    const int fr = red_frame[w];
+    if (fr < 0) { ++w; continue; }
+    double a0 = red[w][0], a1 = red[w][1], a2 = red[w][2], a3 = red[w][3];
+    int e = w + 1;
+    for (; e < kWarps && red_frame[e] == fr; ++e) {
+      a0 = fmin(a0, red[e][0]); a1 = fmin(a1, red[e][1]); a2 = fmax(a2, red[e][2]); a3 = fmax(a3, red[e][3]);
+    }
+    if (a0 <= a2) {   // at least one finite point
+      atomicMin(&bbox[fr * 4 + 0], double_to_ordered(a0));
+      atomicMin(&bbox[fr * 4 + 1], double_to_ordered(a1));
+      atomicMax(&bbox[fr * 4 + 2], double_to_ordered(a2));
+      atomicMax(&bbox[fr * 4 + 3], double_to_ordered(a3));
+    }
+    w = e;
+  }
 }
 
-__global__ void init_bbox_kernel(long long* bbox, int n_frames) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_frames * 4) bbox[i] = (i & 3) < 2 ? 0x7fffffffffffffffLL : (long long)0x8000000000000000ULL;
+// Host -> device upload of the short per-frame tables through kernel parameters (unlike a pageable
+// cudaMemcpyAsync this never synchronises the stream on the host side and can be captured into a CUDA
+// graph), fused with the initialisation of the bounding boxes and of the stage's status flag.
+constexpr int kTableChunk = 160;   // entries of each of the three tables per launch (3 * 160 * 8 = 3840 bytes of parameters)
+struct FrameTableChunk { int64_t frame_ptr[kTableChunk], edge_off[kTableChunk], cell_off[kTableChunk]; };
+__global__ void __launch_bounds__(256)
+init_tables_kernel(const __grid_constant__ FrameTableChunk c, int first, int count, int64_t* __restrict__ frame_ptr,
+                   int64_t* __restrict__ edge_off, int32_t* __restrict__ cell_off, long long* __restrict__ bbox,
+                   int n_frames, int32_t* __restrict__ status) {
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    frame_ptr[first + i] = c.frame_ptr[i];
+    edge_off[first + i] = c.edge_off[i];
+    cell_off[first + i] = static_cast<int32_t>(c.cell_off[i]);
+  }
+  // bounding boxes of the frames this chunk covers (entry j of frame_ptr = start of frame j)
+  for (int i = threadIdx.x; i < count * 4; i += blockDim.x) {
+    const int fr = first + (i >> 2);
+    if (fr < n_frames) bbox[fr * 4 + (i & 3)] = (i & 3) < 2 ? 0x7fffffffffffffffLL : (long long)0x8000000000000000ULL;
+  }
+  if (status != nullptr && first == 0 && threadIdx.x == 0) *status = 0;
 }
 
 // One thread per frame: choose the cell size so that a cell holds ~kPointsPerCell points.
@@ -350,7 +399,10 @@ knn_query_kernel(const T* __restrict__ sorted_pts, const int32_t* __restrict__ s
     if (j < k) {  // slot j is the (k-1-j)-th nearest
       edge_index[e0 + (k - 1 - j)] = i;
       edge_index[n_edges + e0 + (k - 1 - j)] = bi[j];
-      if (in_degree != nullptr) atomicAdd(&in_degree[degree_map != nullptr ? degree_map[bi[j]] : bi[j]], 1);
+      // a slot that never received a candidate (non-finite coordinates: the stage's status flag is set)
+      // still holds its sentinel id and must not be used as an index
+      if (in_degree != nullptr && static_cast<unsigned>(bi[j]) < static_cast<unsigned>(n_points))
+        atomicAdd(&in_degree[degree_map != nullptr ? degree_map[bi[j]] : bi[j]], 1);
     }
   }
 }
@@ -429,27 +481,6 @@ sort_rows_kernel(const int64_t* __restrict__ row_ptr, int64_t n_points, int64_t*
   }
 }
 
-// Host -> device upload of a short table through kernel parameters: unlike a pageable
-// cudaMemcpyAsync this never synchronises the stream on the host side.
-struct I64Chunk { int64_t v[24]; };
-__global__ void upload_chunk_kernel(I64Chunk c, int count, int64_t* dst64, int32_t* dst32) {
-  const int i = threadIdx.x;
-  if (i < count) {
-    if (dst64) dst64[i] = c.v[i];
-    if (dst32) dst32[i] = static_cast<int32_t>(c.v[i]);
-  }
-}
-int upload_i64(int64_t* dst64, const int64_t* src_host, int64_t count, cudaStream_t stream, int32_t* dst32 = nullptr) {
-  for (int64_t off = 0; off < count; off += 24) {
-    I64Chunk c;
-    const int m = static_cast<int>(count - off < 24 ? count - off : 24);
-    for (int i = 0; i < m; ++i) c.v[i] = src_host[off + i];
-    upload_chunk_kernel<<<1, 32, 0, stream>>>(c, m, dst64 ? dst64 + off : nullptr, dst32 ? dst32 + off : nullptr);
-    RGNN_LAUNCH_CHECK();
-  }
-  return RGNN_OK;
-}
-
 int host_frame_tables(const int64_t* frame_ptr_host, int32_t n_frames, int32_t k,
                       int64_t* edge_off, int32_t* cell_off) {
   int64_t e = 0;
@@ -471,7 +502,7 @@ int host_frame_tables(const int64_t* frame_ptr_host, int32_t n_frames, int32_t k
 
 template <typename T>
 int build_cell_lists_t(const T* basis, int32_t dims, const int64_t* frame_ptr_host, int32_t n_frames, int32_t k,
-                       const GraphWorkspace& w, cudaStream_t stream) {
+                       const GraphWorkspace& w, cudaStream_t stream, int32_t* status, bool zero_status) {
   const int64_t n = frame_ptr_host[n_frames] - frame_ptr_host[0];
   RGNN_PROFILE("cell_lists", stream);
   // small per-frame tables: computed on the host, uploaded without a host-side stream sync
@@ -480,18 +511,25 @@ int build_cell_lists_t(const T* basis, int32_t dims, const int64_t* frame_ptr_ho
     std::vector<int32_t> cell_off(n_frames + 1);
     RGNN_RETURN_IF_ERROR(host_frame_tables(frame_ptr_host, n_frames, k, edge_off.data(), cell_off.data()));
     if (cell_off[n_frames] > w.total_cells) return RGNN_ERR_WORKSPACE_TOO_SMALL;
-    RGNN_RETURN_IF_ERROR(upload_i64(w.frame_ptr, frame_ptr_host, n_frames + 1, stream));
-    RGNN_RETURN_IF_ERROR(upload_i64(w.frame_edge_off, edge_off.data(), n_frames + 1, stream));
-    std::vector<int64_t> wide(cell_off.begin(), cell_off.end());
-    RGNN_RETURN_IF_ERROR(upload_i64(nullptr, wide.data(), n_frames + 1, stream, w.frame_cell_off));
+    for (int first = 0; first <= n_frames; first += kTableChunk) {
+      FrameTableChunk c;
+      const int m = n_frames + 1 - first < kTableChunk ? n_frames + 1 - first : kTableChunk;
+      for (int i = 0; i < m; ++i) {
+        c.frame_ptr[i] = frame_ptr_host[first + i];
+        c.edge_off[i] = edge_off[first + i];
+        c.cell_off[i] = cell_off[first + i];
+      }
+      init_tables_kernel<<<1, 256, 0, stream>>>(c, first, m, w.frame_ptr, w.frame_edge_off, w.frame_cell_off, w.bbox,
+                                                n_frames, zero_status ? status : nullptr);
+      RGNN_LAUNCH_CHECK();
+    }
   }
   if (n == 0) return RGNN_OK;
-  init_bbox_kernel<<<div_up(n_frames * 4, 128), 128, 0, stream>>>(w.bbox, n_frames);
-  RGNN_LAUNCH_CHECK();
-  RGNN_CUDA_CHECK(cudaMemsetAsync(w.cell_count, 0, sizeof(int32_t) * (w.total_cells + 1), stream));
-  RGNN_CUDA_CHECK(cudaMemsetAsync(w.cell_cursor, 0, sizeof(int32_t) * (w.total_cells + 1), stream));
+  // cell_count and cell_cursor are adjacent in the workspace: one memset
+  RGNN_CUDA_CHECK(cudaMemsetAsync(w.cell_count, 0, reinterpret_cast<char*>(w.cell_cursor + w.total_cells + 1) -
+                                                       reinterpret_cast<char*>(w.cell_count), stream));
   const unsigned blocks = div_up(n, kThreads);
-  frame_bbox_kernel<T><<<blocks, kThreads, 0, stream>>>(basis, dims, n, w.frame_ptr, n_frames, w.bbox);
+  frame_bbox_kernel<T><<<blocks, kThreads, 0, stream>>>(basis, dims, n, w.frame_ptr, n_frames, w.bbox, status);
   RGNN_LAUNCH_CHECK();
   frame_grid_kernel<<<div_up(n_frames, 64), 64, 0, stream>>>(w.bbox, w.frame_ptr, w.frame_edge_off,
                                                              w.frame_cell_off, n_frames, w.grids);
@@ -572,10 +610,13 @@ int check_graph_args(const void* basis, int32_t basis_dtype, int32_t dims, const
 }  // namespace
 
 int build_cell_lists(const void* basis, int32_t basis_dtype, int32_t dims, const int64_t* frame_ptr_host,
-                     int32_t n_frames, int32_t k, const GraphWorkspace& w, cudaStream_t stream) {
+                     int32_t n_frames, int32_t k, const GraphWorkspace& w, cudaStream_t stream, int32_t* status,
+                     bool zero_status) {
   if (basis_dtype == RGNN_F32)
-    return build_cell_lists_t<float>(static_cast<const float*>(basis), dims, frame_ptr_host, n_frames, k, w, stream);
-  return build_cell_lists_t<double>(static_cast<const double*>(basis), dims, frame_ptr_host, n_frames, k, w, stream);
+    return build_cell_lists_t<float>(static_cast<const float*>(basis), dims, frame_ptr_host, n_frames, k, w, stream,
+                                     status, zero_status);
+  return build_cell_lists_t<double>(static_cast<const double*>(basis), dims, frame_ptr_host, n_frames, k, w, stream,
+                                    status, zero_status);
 }
 
 int knn_query(int32_t basis_dtype, int32_t dims, int64_t n_points, int32_t k, int64_t* edge_index,
@@ -633,8 +674,8 @@ int64_t rgnn_knn_edge_count(const int64_t* frame_ptr_host, int32_t n_frames, int
 }
 
 int rgnn_graph_build_knn(const void* basis, int32_t basis_dtype, int32_t dims, const int64_t* frame_ptr_host,
-                         int32_t n_frames, int32_t k, int64_t* edge_index, int64_t n_edges, void* workspace,
-                         size_t workspace_bytes, rgnn_stream_t stream_) {
+                         int32_t n_frames, int32_t k, int64_t* edge_index, int64_t n_edges, int32_t* error_flag,
+                         void* workspace, size_t workspace_bytes, rgnn_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int64_t n = 0;
   RGNN_RETURN_IF_ERROR(check_graph_args(basis, basis_dtype, dims, frame_ptr_host, n_frames, workspace, workspace_bytes, &n));
@@ -645,7 +686,8 @@ int rgnn_graph_build_knn(const void* basis, int32_t basis_dtype, int32_t dims, c
   Arena arena(workspace, workspace_bytes);
   GraphWorkspace w = carve_graph_workspace(arena, n, n_frames);
   if (arena.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
-  RGNN_RETURN_IF_ERROR(build_cell_lists(basis, basis_dtype, dims, frame_ptr_host, n_frames, k, w, stream));
+  RGNN_RETURN_IF_ERROR(build_cell_lists(basis, basis_dtype, dims, frame_ptr_host, n_frames, k, w, stream,
+                                        error_flag != nullptr ? error_flag : w.status, true));
   return knn_query(basis_dtype, dims, n, k, edge_index, n_edges, nullptr, nullptr, w, stream);
 }
 
@@ -661,14 +703,16 @@ int rgnn_graph_build_radius_count(const void* basis, int32_t basis_dtype, int32_
   GraphWorkspace w = carve_graph_workspace(arena, n, n_frames);
   if (arena.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
   *n_edges_host = 0;
-  RGNN_RETURN_IF_ERROR(build_cell_lists(basis, basis_dtype, dims, frame_ptr_host, n_frames, 0, w, stream));
+  RGNN_RETURN_IF_ERROR(build_cell_lists(basis, basis_dtype, dims, frame_ptr_host, n_frames, 0, w, stream, w.status, true));
   if (n == 0) return RGNN_OK;
   RGNN_RETURN_IF_ERROR(radius_query(false, basis_dtype, dims, n, r, nullptr, 0, w, stream));
   RGNN_RETURN_IF_ERROR(exclusive_scan_i32_to_i64(w.row_count, w.row_ptr, n,
                                                  reinterpret_cast<int64_t*>(w.scan_scratch), stream));
+  int32_t status_host = 0;
   RGNN_CUDA_CHECK(cudaMemcpyAsync(n_edges_host, w.row_ptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  RGNN_CUDA_CHECK(cudaMemcpyAsync(&status_host, w.status, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   RGNN_CUDA_CHECK(cudaStreamSynchronize(stream));
-  return RGNN_OK;
+  return status_host != 0 ? status_host : RGNN_OK;   // RGNN_ERR_NON_FINITE_INPUT
 }
 
 int rgnn_graph_build_radius_fill(const void* basis, int32_t basis_dtype, int32_t dims,

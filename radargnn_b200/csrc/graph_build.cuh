@@ -39,6 +39,7 @@ struct GraphWorkspace {
   int32_t* row_count;      // [N + 1] radius: neighbours per point (original order)
   int64_t* row_ptr;        // [N + 1] radius: exclusive scan
   int32_t* scan_scratch;   // scan_scratch_ints(max(N, cells)) * 2 (int64 variant)
+  int32_t* status;         // [64] device flag of the stage: RGNN_ERR_NON_FINITE_INPUT when a coordinate is NaN / inf
   int32_t total_cells;
 };
 
@@ -56,8 +57,8 @@ inline GraphWorkspace carve_graph_workspace(ArenaT& a, int64_t n, int32_t f) {
   w.grids = a.template take<FrameGrid>(f);
   w.point_cell = a.template take<int32_t>(n);
   w.cell_count = a.template take<int32_t>(cells + 1);
+  w.cell_cursor = a.template take<int32_t>(cells + 1);   // directly after cell_count: both are zeroed by one memset
   w.cell_start = a.template take<int32_t>(cells + 1);
-  w.cell_cursor = a.template take<int32_t>(cells + 1);
   w.sorted_idx = a.template take<int32_t>(n);
   w.sorted_cell = a.template take<int32_t>(n);
   w.sorted_frame = a.template take<int32_t>(n);
@@ -67,14 +68,18 @@ inline GraphWorkspace carve_graph_workspace(ArenaT& a, int64_t n, int32_t f) {
   w.row_ptr = a.template take<int64_t>(n + 1);
   const int64_t m = n > cells ? n : cells;
   w.scan_scratch = a.template take<int32_t>(scan_scratch_ints(m) * 2);
+  w.status = a.template take<int32_t>(64);
   return w;
 }
 
 // Bins the points of all frames into their cell lists (bbox -> grid -> count -> scan -> scatter).
 // `k` > 0 additionally fills frame_edge_off for the k-NN row layout.
+// status (device int32, optional): set to RGNN_ERR_NON_FINITE_INPUT when some coordinate is NaN or infinite
+// (sklearn raises "Input contains NaN"); zeroed first when zero_status is set.
 int build_cell_lists(const void* basis, int32_t basis_dtype, int32_t dims,
                      const int64_t* frame_ptr_host, int32_t n_frames, int32_t k,
-                     const GraphWorkspace& w, cudaStream_t stream);
+                     const GraphWorkspace& w, cudaStream_t stream, int32_t* status = nullptr,
+                     bool zero_status = false);
 
 // k-NN query over the cell lists.  Optional fused outputs (may be null): in-degree
 // histogram of the targets (edge_index[1]) for the CSC build.

@@ -1013,11 +1013,8 @@ int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
   p.a1_tma = (tma_enabled && p.a1_rows == nullptr && encode_panel_map(&p.tm_a1, p.a1, p.m, p.k1, p.lda1)) ? 1 : 0;
   p.at_tma = (tma_enabled && p.at != nullptr && p.kt > 0 && encode_panel_map(&p.tm_at, p.at, p.m, p.kt, p.ldat)) ? 1 : 0;
   const size_t smem = smem_bytes_for(p.np, p.kp, p.raw_slots, p.staged_epilogue);
-  static size_t configured = 0;
-  if (smem > configured) {
-    RGNN_CUDA_CHECK(cudaFuncSetAttribute(node_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = 227 * 1024;
-  }
+  static bool configured[kMaxDevices] = {};
+  RGNN_CUDA_CHECK(opt_in_dynamic_smem(node_gemm_kernel, configured, 227 * 1024));
   const int64_t tiles = (p.m + kRows - 1) / kRows;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   RGNN_PROFILE(tag, stream);

@@ -181,7 +181,8 @@ static int pipeline_forward_impl(const rgnn_pipeline_desc* desc, const float* po
     const int64_t expect = rgnn_knn_edge_count(frame_ptr_host, n_frames, desc->k, &st);
     if (st != RGNN_OK) return st;
     if (expect != n_edges) return RGNN_ERR_INVALID_ARGUMENT;
-    RGNN_RETURN_IF_ERROR(build_cell_lists(basis, RGNN_F32, desc->distance_dims, frame_ptr_host, n_frames, desc->k, w.graph, stream));
+    RGNN_RETURN_IF_ERROR(build_cell_lists(basis, RGNN_F32, desc->distance_dims, frame_ptr_host, n_frames, desc->k, w.graph, stream,
+                                          error_flag, false));   // non-finite coordinates -> RGNN_ERR_NON_FINITE_INPUT
     RGNN_CUDA_CHECK(cudaMemsetAsync(w.csc.count, 0, sizeof(int32_t) * (n + 1), stream));
     RGNN_RETURN_IF_ERROR(knn_query(RGNN_F32, desc->distance_dims, n, desc->k, edge_index, n_edges, w.csc.count,
                                    w.graph.rank, w.graph, stream));
@@ -215,7 +216,7 @@ static int pipeline_forward_impl(const rgnn_pipeline_desc* desc, const float* po
       RGNN_RETURN_IF_ERROR(csc_build_fused(edge_index, n_edges, n, counts_ready, w.csc, w.csc_ptr, w.csc_src, w.csc_eid,
                                            stream, w.graph.rank, fea));
   } else {
-  RGNN_RETURN_IF_ERROR(launch_edge_features(pos, vel, RGNN_F32, 2, 2, edge_index, n_edges, spec, edge_attr, RGNN_F32,
+  RGNN_RETURN_IF_ERROR(launch_edge_features(pos, vel, RGNN_F32, 2, 2, edge_index, n_edges, n, spec, edge_attr, RGNN_F32,
                                             error_flag, stream));
   // The conv stack runs in CELL-SORTED node order (node r = original point sorted_idx[r]): spatial
   // neighbours are then neighbours in memory, so the per-edge gathers of B[source] hit L1 / L2.

@@ -55,6 +55,14 @@ class BatchNorm(torch.nn.Module):
         return ops.affine_relu(x, m.running_mean, scale, beta, relu)
 
 
+def _tensor_version(t: torch.Tensor) -> int:
+    """Version counter of a tensor; inference-mode tensors have none (they cannot be modified in place)."""
+    try:
+        return t._version
+    except RuntimeError:
+        return -1
+
+
 def reset(value) -> None:
     """PyG ``nn.inits.reset``."""
     if hasattr(value, "reset_parameters"):
@@ -73,7 +81,7 @@ class _CscCache:
         self.items: "OrderedDict[tuple, ops.CscGraph]" = OrderedDict()
 
     def get(self, edge_index: torch.Tensor, n_nodes: int) -> ops.CscGraph:
-        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, n_nodes, str(edge_index.device))
+        key = (edge_index.data_ptr(), tuple(edge_index.shape), _tensor_version(edge_index), n_nodes, str(edge_index.device))
         hit = self.items.get(key)
         if hit is not None:
             self.items.move_to_end(key)
@@ -89,18 +97,39 @@ class _CscCache:
 _csc_cache = _CscCache()
 
 
-class MessagePassing(torch.nn.Module):
+def _pyg_message_passing():
+    """``torch_geometric.nn.MessagePassing`` when PyG is importable (the reference's own base class,
+    gnn/mpnn_layers.py:4), else None.  The layers then ARE PyG MessagePassing modules -- ``isinstance``
+    checks, ``jittable`` / hooks and ``aggr`` bookkeeping of a PyG code base keep working -- while
+    ``forward`` still runs the CUDA kernels instead of ``propagate``."""
+    try:
+        from torch_geometric.nn import MessagePassing as base   # noqa: WPS433 (optional dependency)
+        return base
+    except Exception:
+        return None
+
+
+_PygBase = _pyg_message_passing()
+USES_PYG_BASE = _PygBase is not None
+
+
+class MessagePassing(_PygBase if USES_PYG_BASE else torch.nn.Module):
     """The part of PyG's ``MessagePassing`` the reference layers rely on: ``aggr``,
     ``flow = source_to_target`` (``x_j = x[edge_index[0]]``, ``x_i = x[edge_index[1]]``,
-    messages reduced at ``edge_index[1]`` with ``dim_size = x.size(0)``)."""
+    messages reduced at ``edge_index[1]`` with ``dim_size = x.size(0)``).  Subclasses the real PyG class
+    when ``torch_geometric`` is importable, a plain ``torch.nn.Module`` otherwise."""
 
     def __init__(self, aggr: Optional[str] = "add", flow: str = "source_to_target", node_dim: int = -2):
-        super().__init__()
         if flow != "source_to_target":
             raise ValueError("only flow='source_to_target' is implemented (the reference's setting)")
-        self.aggr = aggr
-        self.flow = flow
-        self.node_dim = node_dim
+        if USES_PYG_BASE:
+            super().__init__(aggr=aggr, flow=flow, node_dim=node_dim)
+        else:
+            super().__init__()
+            self.aggr = aggr
+            self.flow = flow
+            self.node_dim = node_dim
+        self.aggr_name = aggr   # PyG >= 2.2 may turn .aggr into an Aggregation module: the kernels take the name
 
     @staticmethod
     def _check_inputs(x: torch.Tensor, edge_index: torch.Tensor, edge_attr: torch.Tensor) -> None:

@@ -15,6 +15,24 @@ def _linears(seq: Sequential):
     return [(m.weight, m.bias) for m in seq if hasattr(m, "weight")]
 
 
+def _cached_params(module, conv_type, c_in, c_out, edge_dim, aggr, pre, post, enc) -> ops.ConvParams:
+    """One ``ops.ConvParams`` per module, kept while the very same weight tensors are installed, so that
+    its packed tensor-core images survive from call to call (they are re-packed when a tensor's address or
+    version counter changes; after an edit through ``.data`` call ``module.invalidate_packed_weights()``)."""
+    tensors = [t for pair in pre + post for t in pair] + (list(enc) if enc is not None else [])
+    key = (conv_type, c_in, c_out, edge_dim, aggr, tuple(id(t) for t in tensors))
+    hit = module.__dict__.get("_conv_params_cache")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    params = ops.ConvParams(conv_type, c_in, c_out, edge_dim, aggr, pre, post, enc)
+    module.__dict__["_conv_params_cache"] = (key, params)
+    return params
+
+
+def _invalidate(module) -> None:
+    module.__dict__.pop("_conv_params_cache", None)
+
+
 def _run_sequential(seq: Sequential, x: Tensor) -> Tensor:
     """Linear [, ReLU, Linear]* on the CUDA linear kernel, each ReLU fused into the next Linear."""
     relu_pending = False
@@ -78,8 +96,13 @@ class MPNNConv(MessagePassing):
         ``layer.weight`` after construction, test/test_gnn.py:13-16)."""
         enc = (self.edge_encoder.weight, self.edge_encoder.bias) if self.use_edge_encoder else None
         post = _linears(self.post_mlp)
-        return ops.ConvParams("MPNNConv", self.in_channels, post[-1][0].shape[0], self.edge_dim, self.aggr,
+        return _cached_params(self, "MPNNConv", self.in_channels, post[-1][0].shape[0], self.edge_dim, self.aggr_name,
                               _linears(self.pre_mlp), post, enc)
+
+    def invalidate_packed_weights(self) -> None:
+        """Drop the cached tensor-core weight images (needed only after edits that bypass the tensors'
+        version counters, e.g. ``w.data.normal_()``)."""
+        _invalidate(self)
 
     def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor) -> Tensor:
         self._check_inputs(x, edge_index, edge_attr)
@@ -133,8 +156,11 @@ class RadarPointGNNConv(MessagePassing):
             reset(nn)
 
     def conv_params(self) -> ops.ConvParams:
-        return ops.ConvParams("RadarPointGNNConv", self.init_node_dim, self.init_node_dim, self.init_edge_dim,
-                              self.aggr, _linears(self.pre_mlp), _linears(self.post_mlp), None)
+        return _cached_params(self, "RadarPointGNNConv", self.init_node_dim, self.init_node_dim, self.init_edge_dim,
+                              self.aggr_name, _linears(self.pre_mlp), _linears(self.post_mlp), None)
+
+    def invalidate_packed_weights(self) -> None:
+        _invalidate(self)
 
     def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor) -> Tensor:
         self._check_inputs(x, edge_index, edge_attr)

@@ -34,9 +34,22 @@ class Graph():
         self.X_feat = None
         self.E_feat = None
         self._A = None
-        self.E = None
+        self._E = None
         self._n = 0
-        self._edge_index_dev: Optional[torch.Tensor] = None  # int64 [2, E] on the device
+        self._edge_index_dev: Optional[torch.Tensor] = None  # int64 [2, E] on the device, mirrors _E
+        self._dev_in_E_order = False   # the device copy lists the edges in E's own row order (set by build())
+
+    # -- edge list: assigning E by hand drops the device copy and the cached adjacency matrix -----
+    @property
+    def E(self):
+        return self._E
+
+    @E.setter
+    def E(self, value):
+        self._E = value
+        self._edge_index_dev = None
+        self._dev_in_E_order = False
+        self._A = None
 
     # -- adjacency matrix, built only when somebody looks at it ----------------------------------
     @property
@@ -63,9 +76,9 @@ class Graph():
 
     def __set_edges(self, X: np.ndarray, edge_index: torch.Tensor) -> None:
         self._n = X.shape[0]
-        self._edge_index_dev = edge_index
         self.E = edge_index.t().contiguous().cpu().numpy()
-        self._A = None
+        self._edge_index_dev = edge_index   # after the setter (which drops any stale device copy)
+        self._dev_in_E_order = True
 
     def __build_knn(self, X: np.ndarray, k: int) -> None:
         basis = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64), device=_device())
@@ -74,6 +87,10 @@ class Graph():
     def __build_rn(self, X: np.ndarray, r: float) -> None:
         basis = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64), device=_device())
         self.__set_edges(X, ops.radius_graph(basis, r))
+
+    def _built_edges_current(self) -> bool:
+        """The device edge_index of the last build() still describes ``E`` (rows in E's order)."""
+        return self._edge_index_dev is not None and self._dev_in_E_order
 
     def add_node_features(self, feat: np.ndarray) -> None:
         if self.X_feat is None:
@@ -85,8 +102,9 @@ class Graph():
                 raise Exception("Feature dimension not compatible")
 
     def _edge_index(self) -> torch.Tensor:
-        if self._edge_index_dev is None or self._edge_index_dev.shape[1] != self.E.shape[0]:
-            # E was assigned by hand: group rows by source for the degree kernel
+        if self._edge_index_dev is None:
+            # E was assigned by hand (or edited in place: callers must re-assign it): group rows by source
+            # for the degree kernel
             E = np.asarray(self.E, dtype=np.int64)
             order = np.lexsort((E[:, 1], E[:, 0]))
             self._edge_index_dev = torch.as_tensor(np.ascontiguousarray(E[order].T), device=_device())
@@ -141,7 +159,7 @@ class GeometricGraph(Graph):
         dev = _device()
         pos = torch.as_tensor(np.ascontiguousarray(self.X, dtype=np.float64), device=dev)
         vel = torch.as_tensor(np.ascontiguousarray(self.V, dtype=np.float64), device=dev)
-        if self._edge_index_dev is not None and self._edge_index_dev.shape[1] == self.E.shape[0]:
+        if self._built_edges_current():
             ei = self._edge_index_dev
         else:
             ei = torch.as_tensor(np.ascontiguousarray(np.asarray(self.E, dtype=np.int64).T), device=dev)
@@ -154,10 +172,20 @@ class GeometricGraph(Graph):
         """Node feature matrix ``X_feat`` [N, Fn], columns in list order (reference graph.py:225-275)."""
         dev = _device()
         n = np.asarray(self.X).shape[0]
-        known = [f for f in features if f in ("rcs", "time_index", "degree", "velocity_vector_length",
-                                              "velocity_vector", "spatial_coordinates")]
-        if "degree" in features:
-            self.add_degree_to_inv_features()
+        if np.asarray(self.X).ndim != 2 or np.asarray(self.X).shape[1] != 2 or np.asarray(self.V).shape != np.asarray(self.X).shape:
+            raise ValueError("X and V must both be [N, 2] arrays (the node-feature kernel reads two columns each)")
+        names = ("rcs", "time_index", "degree", "velocity_vector_length", "velocity_vector", "spatial_coordinates")
+        known = []
+        for f in features:
+            if f in names:
+                known.append(f)
+            elif known:
+                known.append(known[-1])   # reference quirk (graph.py:253-275): an unknown name re-appends the previous feature
+            else:
+                raise UnboundLocalError("local variable 'feat' referenced before assignment")  # what the reference raises
+        for f in features:
+            if f == "degree":
+                self.add_degree_to_inv_features()   # once per occurrence, like the reference (graph.py:246-248)
         F = self.F or {}
 
         def dev_f64(a):

@@ -37,6 +37,14 @@ def _frame_ptr(frame_ptr, n: int) -> np.ndarray:
     return fp
 
 
+def _version_of(t: torch.Tensor) -> int:
+    """torch's in-place version counter; tensors made under inference_mode have none (and cannot change)."""
+    try:
+        return t._version
+    except RuntimeError:
+        return -1
+
+
 def _cuda_contig(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor: radargnn_b200 has no CPU fallback")
@@ -51,7 +59,7 @@ def knn_edge_count(frame_ptr: np.ndarray, k: int) -> int:
     return int(e)
 
 
-def knn_graph(basis: torch.Tensor, k: int, frame_ptr=None) -> torch.Tensor:
+def knn_graph(basis: torch.Tensor, k: int, frame_ptr=None, check_input: bool = True) -> torch.Tensor:
     """k-NN graph of every frame (graph.py:52-66): edge_index int64 [2, E], row 0 the query point,
     row 1 its neighbours by ascending (fp64 squared distance, index)."""
     _lib.require_device()
@@ -61,11 +69,14 @@ def knn_graph(basis: torch.Tensor, k: int, frame_ptr=None) -> torch.Tensor:
     fp = _frame_ptr(frame_ptr, n)
     n_edges = knn_edge_count(fp, k)
     edge_index = torch.empty((2, n_edges), dtype=torch.int64, device=basis.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=basis.device)
     with torch.cuda.device(basis.device):
         ws = _lib.workspace(lib.rgnn_graph_workspace_bytes(n, len(fp) - 1), basis.device)
         _lib.check(lib.rgnn_graph_build_knn(basis.data_ptr(), _dtype_code(basis), dims, fp.ctypes.data,
-                                            len(fp) - 1, int(k), edge_index.data_ptr(), n_edges,
+                                            len(fp) - 1, int(k), edge_index.data_ptr(), n_edges, flag.data_ptr(),
                                             ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    if check_input:
+        _lib.check(int(flag.item()))   # sklearn: ValueError("Input contains NaN")
     return edge_index
 
 
@@ -187,10 +198,12 @@ def csc_build(edge_index: torch.Tensor, n_nodes: int) -> CscGraph:
     ptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=dev)
     src = torch.empty(n_edges, dtype=torch.int32, device=dev)
     eid = torch.empty(n_edges, dtype=torch.int32, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         ws = _lib.workspace(lib.rgnn_csc_workspace_bytes(n_nodes, n_edges), dev)
         _lib.check(lib.rgnn_csc_build(edge_index.data_ptr(), n_edges, n_nodes, ptr.data_ptr(), src.data_ptr(),
-                                      eid.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+                                      eid.data_ptr(), flag.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    _lib.check(int(flag.item()))   # an id outside [0, N) raises like PyG's gather does
     return CscGraph(ptr, src, eid, n_nodes, n_edges)
 
 
@@ -206,9 +219,13 @@ class ConvParams:
     post: List[Tuple[torch.Tensor, torch.Tensor]]
     edge_encoder: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
     # tensor-core weight images, rebuilt only when a weight tensor was replaced or modified in place
-    # (the key holds every tensor's address and torch version counter)
+    # (the key holds every tensor's address and torch version counter).  Edits through ``.data`` bypass the
+    # version counter: call invalidate() after them (a held PipelineConfig / ConvParams keeps its images).
     _packed: Optional[torch.Tensor] = None
     _packed_key: Optional[tuple] = None
+
+    def invalidate(self) -> None:
+        self._packed, self._packed_key = None, None
 
     def _tensors(self):
         out = [t for pair in self.pre + self.post for t in pair]
@@ -247,7 +264,7 @@ class ConvParams:
             lib = _lib.load()
             nbytes = lib.rgnn_conv_packed_bytes(C.byref(d))
             if nbytes > 0:
-                key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in self._tensors()) + (self.aggr,)
+                key = tuple((t.data_ptr(), _version_of(t), tuple(t.shape)) for t in self._tensors()) + (self.aggr,)
                 if self._packed is None or self._packed_key != key or self._packed.numel() < nbytes:
                     device = self.pre[0][0].device
                     buf = torch.empty(nbytes, dtype=torch.uint8, device=device)

@@ -41,11 +41,13 @@ def test_every_entry_point_cites_the_reference():
 
 
 def test_status_strings_match_reference_messages(lib):
-    assert lib.rgnn_abi_version() == 1
+    assert lib.rgnn_abi_version() == 2
     assert lib.rgnn_status_string(0) == b"ok"
     assert lib.rgnn_status_string(2) == b"Expected n_neighbors < n_samples_fit"   # sklearn's ValueError text
     assert lib.rgnn_status_string(5) == b"Error in dot product calculation"        # features.py:56
     assert lib.rgnn_status_string(6) == b"Invalid feature specified"               # graph.py:220
+    assert lib.rgnn_status_string(9) == b"Input contains NaN or infinity"          # sklearn check_array
+    assert b"outside [0, N)" in lib.rgnn_status_string(10)
 
 
 def test_knn_edge_count_and_k_check(lib):
@@ -108,9 +110,9 @@ def test_compute_entry_points_fail_loudly_without_a_device(lib):
 
 
 def test_product_never_imports_the_oracle():
-    pkg = os.path.join(ROOT, "radargnn_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith(".py"):
-                src = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), f"{f} mentions the oracle"
+    for pkg in (os.path.join(ROOT, "radargnn_b200"), os.path.join(ROOT, "src")):
+        for dirpath, _, files in os.walk(pkg):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), f"{f} mentions the oracle"

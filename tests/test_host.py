@@ -119,3 +119,88 @@ def test_loss_all_reduce_two_ranks_gloo():
 def test_all_reduce_loss_single_process():
     from radargnn_b200.sharding import all_reduce_loss
     assert float(all_reduce_loss(torch.tensor(6.0), torch.tensor(4.0))) == 1.5
+
+
+# ---- the reference's own import paths (BASELINE.json north star: "drop in under src/gnnradarobjectdetection") ----
+def test_reference_import_paths_resolve_to_the_cuda_backed_classes():
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from gnnradarobjectdetection.gnn.mpnn_layers import MPNNConv, RadarPointGNNConv\n"
+        "from gnnradarobjectdetection.gnn.gnn_models import DetNetBasic, get_mlp\n"
+        "from gnnradarobjectdetection.gnn.configs import GNNArchitectureConfig\n"
+        "from gnnradarobjectdetection.graph_constructor.graph import Graph, GeometricGraph\n"
+        "from gnnradarobjectdetection.graph_constructor.features import get_En_equivariant_point_pair_metrics\n"
+        "from gnnradarobjectdetection.preprocessor.configs import GraphConstructionConfiguration\n"
+        "from gnnradarobjectdetection.preprocessor.radar_point_cloud import RadarPointCloud\n"
+        "from gnnradarobjectdetection.preprocessor.radarscenes.dataset_creation import GraphConstructor, create_graph_data\n"
+        "from gnnradarobjectdetection.preprocessor.nuscenes.conversion import build_geometric_graph\n"
+        "import radargnn_b200.gnn.mpnn_layers as impl, radargnn_b200.ops as ops\n"
+        "assert MPNNConv is impl.MPNNConv and RadarPointGNNConv is impl.RadarPointGNNConv\n"
+        "import inspect; assert 'ops.conv_forward' in inspect.getsource(MPNNConv.forward)\n"
+        "print('ok')\n") % os.path.join(root, "src")
+    # run from another directory: the package must find radargnn_b200 by itself
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
+
+
+def test_layers_subclass_the_real_pyg_message_passing_when_it_is_importable(tmp_path):
+    """The reference's layers subclass torch_geometric.nn.MessagePassing (gnn/mpnn_layers.py:4,11).  PyG is
+    not installed here, so a minimal stand-in package proves the wiring: with torch_geometric importable the
+    CUDA-backed layers must BE MessagePassing modules, without it they are plain torch modules."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = tmp_path / "torch_geometric"
+    (pkg / "nn").mkdir(parents=True)
+    (pkg / "__init__.py").write_text("__version__ = 'stub'\n")
+    (pkg / "nn" / "__init__.py").write_text(
+        "import torch\n"
+        "class MessagePassing(torch.nn.Module):\n"
+        "    def __init__(self, aggr='add', flow='source_to_target', node_dim=-2):\n"
+        "        super().__init__()\n"
+        "        self.aggr, self.flow, self.node_dim = aggr, flow, node_dim\n")
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import torch_geometric.nn as tgnn\n"
+        "from radargnn_b200.gnn import MPNNConv, RadarPointGNNConv\n"
+        "from radargnn_b200.gnn import _message_passing as mp\n"
+        "assert mp.USES_PYG_BASE\n"
+        "c = MPNNConv(2, 4, 3, aggr='max'); r = RadarPointGNNConv(2, 1)\n"
+        "assert isinstance(c, tgnn.MessagePassing) and isinstance(r, tgnn.MessagePassing)\n"
+        "assert c.aggr == 'max' and c.conv_params().aggr == 'max' and c.pre_mlp[0].weight.shape == (7, 7)\n"
+        "print('ok')\n") % (root, str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
+    from radargnn_b200.gnn import _message_passing as mp
+    if not mp.USES_PYG_BASE:   # this interpreter has no PyG: plain torch module
+        from radargnn_b200.gnn import MPNNConv
+        assert isinstance(MPNNConv(2, 4, 3), torch.nn.Module)
+
+
+def test_conv_params_are_cached_per_module_and_follow_reassigned_weights():
+    from radargnn_b200.gnn import MPNNConv
+    conv = MPNNConv(2, 4, 3)
+    a = conv.conv_params()
+    assert conv.conv_params() is a                      # same tensors installed: same object (keeps packed images)
+    conv.post_mlp[0].weight = torch.nn.Parameter(torch.zeros_like(conv.post_mlp[0].weight))
+    b = conv.conv_params()
+    assert b is not a and float(b.post[0][0].abs().sum()) == 0.0
+    conv.invalidate_packed_weights()
+    assert conv.conv_params() is not b
+    with torch.inference_mode():
+        t = torch.ones(3)
+    from radargnn_b200 import ops
+    assert ops._version_of(t) == -1                     # no version counter under inference_mode: must not raise
+
+
+def test_graph_edge_list_setter_drops_stale_device_state():
+    from radargnn_b200.graph_constructor.graph import Graph
+    g = Graph()
+    g._edge_index_dev, g._dev_in_E_order, g._A = object(), True, object()
+    g.E = np.array([[0, 1], [1, 0]])
+    assert g._edge_index_dev is None and g._A is None and not g._built_edges_current()
+    g._n = 2
+    assert g.A.tolist() == [[0.0, 1.0], [1.0, 0.0]]
