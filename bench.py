@@ -11,8 +11,9 @@ only all-reduce the loss scalar (NCCL).  One JSON line is printed by rank 0:
   value        whole-job edges/s with the inputs already resident in HBM (CUDA-event timed, L2 flushed
                between steps, max over ranks);
   e2e          the same metric through the host-buffer C-ABI entry point (rgnn_pipeline_forward_host):
-               H2D of pos / vel / x0 from pinned memory and D2H of the node embeddings inside the timed
-               region;
+               H2D of pos / vel / x0 from pinned memory and D2H of EVERY output of the path (edge_index,
+               edge_attr and the node embeddings) inside the timed region;  e2e_embeddings_only: the same call
+               downloading only the node embeddings (the graph stays on the device);
   roofline     dominant kernel: algorithmic bytes per launch / measured device time per launch, against
                MEASURED_PEAKS.json:hbm_gbs;  path_roofline: the whole step against SURVEY.md 8(d)'s B_alg;
   cpu_baseline the CPU port of the reference path (oracle/) on a bounded sample, rank 0 / N = 1 only.
@@ -37,16 +38,48 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# BASELINE.json configs as SURVEY.md section 8(d) defines them.  frames / points are PER GPU (weak scaling).
 WORKLOADS = {
-    # name: frames per GPU, points per frame, k, layers, channels, generator
-    "headline_100k_k16_4x64": dict(frames=1, points=100_000, k=16, layers=4, channels=64, gen="uniform"),
-    "config2_10k_k16_4x64": dict(frames=1, points=10_000, k=16, layers=4, channels=64, gen="uniform"),
-    "config3_64x300_k20_8x128": dict(frames=64, points=300, k=20, layers=8, channels=128, gen="radar"),
-    "config5_125k_k16_4x64": dict(frames=1, points=125_000, k=16, layers=4, channels=64, gen="uniform"),
+    "headline_100k_k16_4x64": dict(frames=1, points=100_000, search="knn", k=16, layers=4, c0=64, channels=64,
+                                   gen="uniform", edge_features=["relative_position"]),
+    "config1_300_r3_1x64": dict(frames=1, points=300, search="radius", r=3.0, k=6, layers=1, c0=5, channels=64,
+                                gen="radar", edge_features=["relative_position"]),
+    "config2_10k_k16_4x64": dict(frames=1, points=10_000, search="knn", k=16, layers=4, c0=64, channels=64,
+                                 gen="uniform", edge_features=["relative_position"]),
+    "config3_64x300_k20_8x128": dict(frames=64, points=300, search="knn", k=20, layers=8, c0=128, channels=128,
+                                     gen="radar", edge_features=["relative_position"]),
+    "config4_64x2000_k20_ppf_4x64": dict(frames=64, points=2000, search="knn", k=20, layers=4, c0=64, channels=64,
+                                         gen="nuscenes", edge_features=["point_pair_features"]),
+    "config5_125k_k16_4x64": dict(frames=1, points=125_000, search="knn", k=16, layers=4, c0=64, channels=64,
+                                  gen="uniform", edge_features=["relative_position"]),
 }
 DEFAULT_WORKLOAD = "headline_100k_k16_4x64"
-EDGE_FEATURES = ["relative_position"]   # translation-invariant edge_attr, De = 2
-CPU_SAMPLE_POINTS = 10_000               # CPU baseline runs the reference path on this many points
+# The CPU arm runs the reference's path on ONE frame of at most this many points: the per-edge Python loop
+# (graph.py:172-223) costs ~8 us (relative_position) to ~200 us (point-pair features) per edge, i.e. 17 s to
+# minutes per step at the full 100 k points, and the driver times --steps 20 --warmup 5 of it.  Its cost
+# per edge does not depend on the frame size, so edges/s of the sample is the rate of the full workload.
+CPU_SAMPLE_POINTS = 25_000
+CPU_SAMPLE_POINTS_PPF = 2_000
+
+
+def edge_dim(wl: dict) -> int:
+    return sum(4 if f == "point_pair_features" else 2 if f in ("relative_position", "relative_velocity") else 1
+               for f in wl["edge_features"])
+
+
+def metric_name(wl: dict) -> str:
+    return f"edges/s: graph-build + {wl['layers']}-layer MPNN fwd"
+
+
+def workload_config(name: str, wl: dict, world: int) -> dict:
+    """The `config` object of the JSON line: identical for the GPU arm and the reference arm."""
+    de = edge_dim(wl)
+    return {"workload": name, "frames_per_gpu": wl["frames"], "points_per_frame": wl["points"],
+            "points_per_gpu": wl["frames"] * wl["points"], "search": wl["search"],
+            "k": wl["k"] if wl["search"] == "knn" else None, "r": wl.get("r") if wl["search"] == "radius" else None,
+            "layers": wl["layers"], "in_channels": wl["c0"], "channels": wl["channels"],
+            "edge_attr": "+".join(wl["edge_features"]) + f" (De={de})", "aggr": "max",
+            "parallelism": f"dp{world} (frames)"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -59,10 +92,12 @@ def make_frames(wl: dict, rank: int):
         seed = rank * 1000 + f
         if wl["gen"] == "uniform":
             frames.append(synthetic.uniform_square(wl["points"], seed=seed))
+        elif wl["gen"] == "nuscenes":
+            frames.append(synthetic.nuscenes_frame(wl["points"], seed=seed))
         else:
             frames.append(synthetic.radar_frame(wl["points"], seed=seed))
     X, V, ptr = synthetic.frame_batch(frames)
-    x0 = synthetic.node_embeddings(X.shape[0], wl["channels"], seed=rank)
+    x0 = synthetic.node_embeddings(X.shape[0], wl["c0"], seed=rank)
     return X.astype(np.float32), V.astype(np.float32), ptr, x0
 
 
@@ -70,8 +105,7 @@ def make_params(wl: dict, seed: int = 0):
     """PyG-default initialised MPNNConv stack (uniform(+-1/sqrt(fan_in))), reference key names."""
     import torch
     g = torch.Generator().manual_seed(seed)
-    c, de = wl["channels"], 2
-    p = 2 * c + de
+    c, de = wl["channels"], edge_dim(wl)
     params = {}
 
     def lin(key, o, i):
@@ -79,31 +113,39 @@ def make_params(wl: dict, seed: int = 0):
         params[key + ".weight"] = (torch.rand(o, i, generator=g) * 2 - 1) * b
         params[key + ".bias"] = (torch.rand(o, generator=g) * 2 - 1) * b
 
+    cin = wl["c0"]
     for l in range(wl["layers"]):
+        p = 2 * cin + de
         lin(f"convs.{l}.pre_mlp.0", p, p)
-        lin(f"convs.{l}.post_mlp.0", c, p + c)
+        lin(f"convs.{l}.post_mlp.0", c, p + cin)
         params[f"batch_norms.{l}.module.weight"] = torch.ones(c)
         params[f"batch_norms.{l}.module.bias"] = torch.zeros(c)
+        cin = c
     return params
 
 
 def algorithmic_bytes(n: int, e: int, wl: dict) -> int:
     """B_alg = B_build + sum_l B_layer, every tensor at its API dtype."""
-    c, de, layers = wl["channels"], 2, wl["layers"]
+    c, de, layers = wl["channels"], edge_dim(wl), wl["layers"]
     build = 16 * n + 16 * e + 4 * de * e
-    layer = 4 * n * c + 16 * e + 4 * de * e + 4 * n * c
-    return build + layers * layer
+    total, cin = build, wl["c0"]
+    for _ in range(layers):
+        total += 4 * n * cin + 16 * e + 4 * de * e + 4 * n * c
+        cin = c
+    return total
 
 
 def kernel_algorithmic_bytes(name: str, n: int, e: int, wl: dict):
     """Compulsory bytes of ONE launch of a kernel family ("Kernels"): every input and
-    output touched once at unique-row granularity, weights ignored."""
-    c, de = wl["channels"], 2
+    output touched once at unique-row granularity, weights ignored (channels of the stack's inner layers)."""
+    c, de = wl["channels"], edge_dim(wl)
     p = 2 * c + de
     pp = (p + 3) // 4 * 4
     table = {
         # B rows (unique) + slot sources + slot edge attributes + row pointers + M rows
         "edge_aggregate": 4 * n * pp + 4 * e + 4 * de * e + 4 * (n + 1) + 4 * n * pp,
+        # fused aggregate + node update: B rows (unique) + slot sources / attributes / row pointers + x + h
+        "edge_update_fused": 4 * n * pp + 4 * e + 4 * de * e + 4 * (n + 1) + 4 * n * c + 4 * n * c,
         "node_gemm_pre": 4 * n * c + 4 * n * pp,             # read x, write B = x W_s^T
         "node_gemm_post": 4 * n * c + 4 * n * pp + 4 * n * c,  # read x and M, write h
         "linear_pre_node": 4 * n * c + 4 * n * pp,
@@ -111,6 +153,7 @@ def kernel_algorithmic_bytes(name: str, n: int, e: int, wl: dict):
         "knn_query": 8 * n + 16 * n + 16 * e + 4 * n,        # sorted points + ids/cells + edge_index + in-degree
         "bn_statistics": 4 * n * c,
         "edge_features": 16 * e + 16 * n + 4 * de * e,
+        "csc_build_edge_attr": 16 * e + 8 * e + 2 * 4 * de * e + 16 * n,
     }
     return table.get(name)
 
@@ -119,23 +162,35 @@ def kernel_algorithmic_bytes(name: str, n: int, e: int, wl: dict):
 # CPU port of the reference path (the only place bench.py executes oracle/)
 # ---------------------------------------------------------------------------------------------
 def cpu_reference_step(sample, params, wl):
-    """The reference's CPU path on one frame: sklearn k-NN (graph.py:57-63, 1 thread), the per-edge
-    Python feature loop (graph.py:172-223), then the PyG-equivalent MPNN forward on all cores."""
+    """The reference's CPU path on one frame: sklearn k-NN / radius (graph.py:57-63 / 73-79, 1 thread), the
+    per-edge Python feature loop (graph.py:172-223), then the PyG-equivalent MPNN forward on all cores."""
     import torch
     from oracle import mpnn_oracle, reference_loop
     X, V, x0 = sample
-    E, _ = reference_loop.build_edges_like_reference(X, "knn", wl["k"], 0.0, dense=False)
-    ef = reference_loop.edge_feature_loop(X, V, E, EDGE_FEATURES, "directed")
+    E, _ = reference_loop.build_edges_like_reference(X, wl["search"], wl["k"], wl.get("r", 0.0), dense=False)
+    ef = reference_loop.edge_feature_loop(X, V, E, wl["edge_features"], "directed")
     with torch.no_grad():
         h = mpnn_oracle.conv_stack_forward(params, torch.from_numpy(x0), torch.from_numpy(E.T.astype(np.int64)),
                                            torch.from_numpy(ef.astype(np.float32)), wl["layers"], "MPNNConv", "max")
     return E.shape[0], float(h.mean())
 
 
+def cpu_sample_points(wl) -> int:
+    cap = CPU_SAMPLE_POINTS_PPF if "point_pair_features" in wl["edge_features"] else CPU_SAMPLE_POINTS
+    return min(wl["points"], cap)
+
+
 def cpu_sample(wl):
+    """One frame of the workload's generator (same density, same k / r, same layer stack)."""
     from radargnn_b200 import synthetic
-    fr = synthetic.uniform_square(CPU_SAMPLE_POINTS, seed=12345)
-    return fr.X_cc, fr.V_cc_compensated, synthetic.node_embeddings(CPU_SAMPLE_POINTS, wl["channels"], seed=3)
+    n = cpu_sample_points(wl)
+    if wl["gen"] == "uniform":
+        fr = synthetic.uniform_square(n, seed=12345)
+    elif wl["gen"] == "nuscenes":
+        fr = synthetic.nuscenes_frame(n, seed=12345)
+    else:
+        fr = synthetic.radar_frame(n, seed=12345)
+    return fr.X_cc, fr.V_cc_compensated, synthetic.node_embeddings(n, wl["c0"], seed=3)
 
 
 def run_cpu_baseline(wl, steps: int, warmup: int):
@@ -147,6 +202,7 @@ def run_cpu_baseline(wl, steps: int, warmup: int):
         pass
     params = make_params(wl)
     sample = cpu_sample(wl)
+    n = cpu_sample_points(wl)
     for _ in range(warmup):
         cpu_reference_step(sample, params, wl)
     t0 = time.perf_counter()
@@ -155,11 +211,15 @@ def run_cpu_baseline(wl, steps: int, warmup: int):
         e, _ = cpu_reference_step(sample, params, wl)
         edges += e
     dt = time.perf_counter() - t0
+    full = wl["frames"] * wl["points"]
+    why = ("the whole per-GPU workload" if n == full else
+           f"one frame of {n} of the workload's {full} points per GPU (same generator, density, search and layer "
+           f"stack): the reference's per-edge Python loop makes a full-size step take tens of seconds to minutes, "
+           f"and its cost per edge does not depend on the frame size")
     return dict(value=edges / dt, unit="edges/s", cores=int(torch.get_num_threads()), kind="port",
-                sample=(f"{CPU_SAMPLE_POINTS} of the workload's points (one frame, same density, k={wl['k']}, "
-                        f"{wl['layers']}x{wl['channels']}): sklearn k-NN 1 thread + per-edge Python feature loop "
-                        f"+ torch-CPU MPNN forward on all cores; {steps} steps"),
-                ms_per_step=dt / steps * 1e3, host_cpus=os.cpu_count())
+                sample=(f"{why}; sklearn {wl['search']} search 1 thread + per-edge Python feature loop + torch-CPU "
+                        f"MPNN forward ({wl['layers']}x{wl['channels']}) on all cores; {steps} steps"),
+                ms_per_step=dt / steps * 1e3, host_cpus=os.cpu_count(), sample_points=n)
 
 
 def main_reference(args, wl):
@@ -167,17 +227,17 @@ def main_reference(args, wl):
     if rank != 0:
         return 0
     steps = max(1, args.steps)
-    warmup = max(0, min(args.warmup, 3))
+    warmup = max(0, args.warmup)
     base = run_cpu_baseline(wl, steps, warmup)
     line = {
-        "impl": "reference", "metric": "edges/s: graph-build + 4-layer MPNN fwd", "value": base["value"],
+        "impl": "reference", "metric": metric_name(wl), "value": base["value"],
         "unit": "edges/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (graph build in f64)", "data": "synthetic",
-        "config": {"workload": args.workload, "cpu_sample_points": CPU_SAMPLE_POINTS},
+        "config": workload_config(args.workload, wl, args.gpus),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "cpu_sample_points": base["sample_points"],
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -236,14 +296,43 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this process to the CPUs of the NUMA node the GPU's PCIe root hangs off BEFORE any pinned host
+    buffer is allocated (first touch places the pages): the e2e leg's copies then stay node-local.
+    Returns (numa node or None, pci bus id or None)."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
+        bus = out.lower()
+        if bus.startswith("00000000:"):
+            bus = "0000:" + bus[len("00000000:"):]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None, bus
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node, bus
+    except Exception:
+        return None, None
+
+
 def main_gpu(args, wl):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_node, pci_bus = bind_to_gpu_numa_node(local_rank)
+
     import torch
     import torch.distributed as dist
     from radargnn_b200 import _lib, ops
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: radargnn_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -259,16 +348,21 @@ def main_gpu(args, wl):
     pos_h, vel_h, x0_h = (torch.from_numpy(a).pin_memory() for a in (X, V, x0))
     pos_d, vel_d, x0_d = pos_h.to(dev), vel_h.to(dev), x0_h.to(dev)
     params = make_params(wl)
+    de = edge_dim(wl)
     layers, bn = [], []
+    cin = wl["c0"]
     for l in range(wl["layers"]):
         pre = [(params[f"convs.{l}.pre_mlp.0.weight"].to(dev), params[f"convs.{l}.pre_mlp.0.bias"].to(dev))]
         post = [(params[f"convs.{l}.post_mlp.0.weight"].to(dev), params[f"convs.{l}.post_mlp.0.bias"].to(dev))]
-        layers.append(ops.ConvParams("MPNNConv", wl["channels"], wl["channels"], 2, "max", pre, post))
+        layers.append(ops.ConvParams("MPNNConv", cin, wl["channels"], de, "max", pre, post))
         bn.append((params[f"batch_norms.{l}.module.weight"].to(dev), params[f"batch_norms.{l}.module.bias"].to(dev)))
-    cfg = ops.PipelineConfig(layers=layers, bn=bn, algorithm="knn", k=wl["k"], edge_features=EDGE_FEATURES)
+        cin = wl["channels"]
+    cfg = ops.PipelineConfig(layers=layers, bn=bn, algorithm=wl["search"], k=wl["k"], r=wl.get("r", 1.0),
+                             edge_features=wl["edge_features"])
     handle = ops._PipelineHandle(cfg)
     n_frames = len(ptr) - 1
-    n_edges = ops.knn_edge_count(ptr, wl["k"])
+    knn = wl["search"] == "knn"
+    n_edges = ops.knn_edge_count(ptr, wl["k"]) if knn else ops._pipeline_edge_count(cfg, pos_d, vel_d, ptr)
     c_last = wl["channels"]
 
     edge_index = torch.empty((2, n_edges), dtype=torch.int64, device=dev)
@@ -279,17 +373,28 @@ def main_gpu(args, wl):
     sum_ws = _lib.workspace(lib.rgnn_sum_workspace_bytes(), dev)
     loss = torch.zeros(2, dtype=torch.float64, device=dev)   # [sum of h, element count]
     loss[1] = float(n * c_last)
+    loss_global = torch.zeros(1, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
 
-    def step_device():
+    def step_kernels():
+        cur = torch.cuda.current_stream().cuda_stream
         _lib.check(lib.rgnn_pipeline_forward(C.byref(handle.desc), pos_d.data_ptr(), vel_d.data_ptr(), x0_d.data_ptr(),
                                              ptr.ctypes.data, n_frames, edge_index.data_ptr(), n_edges,
                                              edge_attr.data_ptr(), h.data_ptr(), flag.data_ptr(), ws.data_ptr(),
-                                             ws.numel(), sp))
-        _lib.check(lib.rgnn_sum_f32(h.data_ptr(), h.numel(), loss.data_ptr(), sum_ws.data_ptr(), sum_ws.numel(), sp))
+                                             ws.numel(), cur))
+        _lib.check(lib.rgnn_sum_f32(h.data_ptr(), h.numel(), loss.data_ptr(), sum_ws.data_ptr(), sum_ws.numel(), cur))
+
+    def all_reduce_loss():
+        # the path's only collective: the loss scalar over NVLink (NCCL).  The reduced copy is a separate
+        # buffer so that the graph-replayed producer never races with the in-place all-reduce.
+        loss_global.copy_(loss[:1])
+        dist.all_reduce(loss_global)
+
+    def step_device():
+        step_kernels()
         if world > 1:
-            dist.all_reduce(loss[:1])   # the path's only collective: the loss scalar over NVLink
+            all_reduce_loss()
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -322,28 +427,35 @@ def main_gpu(args, wl):
         step_device()
     barrier()
     count0 = _lib.launch_count()
-    step_device()
+    step_kernels()
     launches_per_step = _lib.launch_count() - count0   # kernels of librgnn_b200.so in one step
-    # The ~40 launches of a step are captured once into a CUDA graph and replayed: the first kernels of a
-    # step (14 short cell-list launches) are otherwise bound by host launch latency, not by the GPU.
+    # The launches of a step are captured once into a CUDA graph and replayed: the first kernels of a step
+    # (short cell-list launches) are otherwise bound by host launch latency, not by the GPU.  With N > 1 the
+    # NCCL all-reduce of the loss is captured into the same graph (no eager launch gap after the replay).
+    # A radius search hands its edge count to the host inside the call and cannot be captured.
     step_eager = step_device
     graph = None
-    if not args.no_graph:
-        def step_kernels():
-            _lib.check(lib.rgnn_pipeline_forward(C.byref(handle.desc), pos_d.data_ptr(), vel_d.data_ptr(), x0_d.data_ptr(),
-                                                 ptr.ctypes.data, n_frames, edge_index.data_ptr(), n_edges,
-                                                 edge_attr.data_ptr(), h.data_ptr(), flag.data_ptr(), ws.data_ptr(),
-                                                 ws.numel(), torch.cuda.current_stream().cuda_stream))
-            _lib.check(lib.rgnn_sum_f32(h.data_ptr(), h.numel(), loss.data_ptr(), sum_ws.data_ptr(), sum_ws.numel(),
-                                        torch.cuda.current_stream().cuda_stream))
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            step_kernels()
+    graph_has_collective = False
+    if not args.no_graph and knn:
+        if world > 1 and not args.no_graph_collective:
+            try:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2):
+                    step_kernels()
+                    all_reduce_loss()
+                graph, graph_has_collective = g2, True
+            except Exception:
+                torch.cuda.synchronize()
+                graph = None
+        if graph is None:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step_kernels()
 
         def step_device():
             graph.replay()
-            if world > 1:
-                dist.all_reduce(loss[:1])
+            if world > 1 and not graph_has_collective:
+                all_reduce_loss()
         for _ in range(3):
             step_device()
         barrier()
@@ -354,30 +466,42 @@ def main_gpu(args, wl):
     t_dev = max_over_ranks(t_dev)
     if int(flag.item()) != 0:
         _lib.check(int(flag.item()))
-    loss_value = float(loss[0].item() / (loss[1].item() * world)) if world > 1 else float(loss[0].item() / loss[1].item())
+    loss_value = float(loss_global[0].item() / (loss[1].item() * world)) if world > 1 else float(loss[0].item() / loss[1].item())
 
     # ---- e2e: host buffers through the C-ABI host entry point --------------------------------------
     h_host = torch.empty((n, c_last), dtype=torch.float32).pin_memory()
+    ei_host = torch.empty((2, n_edges), dtype=torch.int64).pin_memory()
+    ea_host = torch.empty((n_edges, handle.edge_dim), dtype=torch.float32).pin_memory()
     host_ws = _lib.workspace(lib.rgnn_pipeline_host_workspace_bytes(C.byref(handle.desc), n, n_frames, n_edges,
-                                                                      wl["channels"]), dev)
+                                                                      wl["c0"]), dev)
 
-    def step_host():
-        _lib.check(lib.rgnn_pipeline_forward_host(
-            C.byref(handle.desc), pos_h.data_ptr(), vel_h.data_ptr(), x0_h.data_ptr(), wl["channels"],
-            ptr.ctypes.data, n_frames, None, n_edges, None, h_host.data_ptr(), host_ws.data_ptr(), host_ws.numel(), sp))
-        if world > 1:
-            part = torch.tensor([float(h_host[0, 0])], dtype=torch.float64, device=dev)
-            dist.all_reduce(part)
+    def make_step_host(full: bool):
+        ei_p = ei_host.data_ptr() if full else None
+        ea_p = ea_host.data_ptr() if full else None
 
-    for _ in range(3):
-        step_host()
-    barrier()
+        def step_host():
+            _lib.check(lib.rgnn_pipeline_forward_host(
+                C.byref(handle.desc), pos_h.data_ptr(), vel_h.data_ptr(), x0_h.data_ptr(), wl["c0"],
+                ptr.ctypes.data, n_frames, ei_p, n_edges, ea_p, h_host.data_ptr(), host_ws.data_ptr(), host_ws.numel(), sp))
+            if world > 1:
+                all_reduce_loss()   # persistent device scalars: no allocation, no host sync per step
+        return step_host
+
     e2e_steps = max(3, min(args.steps, 20))
-    t_e2e = timed(step_host, e2e_steps)
-    barrier()
-    t_e2e = max_over_ranks(t_e2e)
-    h2d = int(pos_h.numel() * 4 + vel_h.numel() * 4 + x0_h.numel() * 4)
-    d2h = int(h_host.numel() * 4)
+    e2e = {}
+    for key, full in (("e2e", True), ("e2e_embeddings_only", False)):
+        fn = make_step_host(full)
+        for _ in range(3):
+            fn()
+        barrier()
+        t = max_over_ranks(timed(fn, e2e_steps))
+        barrier()
+        d2h = int(h_host.numel() * 4 + (ei_host.numel() * 8 + ea_host.numel() * 4 if full else 0))
+        e2e[key] = {"value": n_edges * world * e2e_steps / t, "unit": "edges/s",
+                    "h2d_bytes_per_step": int(pos_h.numel() * 4 + vel_h.numel() * 4 + x0_h.numel() * 4),
+                    "d2h_bytes_per_step": d2h, "ms_per_step": t / e2e_steps * 1e3,
+                    "api": "rgnn_pipeline_forward_host (pinned host buffers)",
+                    "outputs": "edge_index + edge_attr + node embeddings" if full else "node embeddings"}
 
     # ---- roofline of the dominant kernel: per-kernel CUDA events over the same steps ----------------
     _lib.profile_reset()
@@ -405,34 +529,41 @@ def main_gpu(args, wl):
         top = max(totals.items(), key=lambda kv: kv[1][0]) if totals else (None, (0.0, 0))
         kname, (kms, kcount) = top
         kbytes = kernel_algorithmic_bytes(kname, n, n_edges, wl) if kname else None
-        traffic = None
+        traffic, traffic_source = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-                traffic = json.load(fh).get(args.workload, {}).get(kname)
+                tj = json.load(fh)
+            traffic = tj.get(args.workload, {}).get(kname)
+            if traffic is not None:
+                traffic_source = tj.get("_source", "profiles/ncu_traffic.json (static: one ncu --set full capture, not this run)")
         except (OSError, ValueError):
             pass
         roofline = None
         if kname and kbytes and kcount:
             achieved = kbytes / (kms / kcount * 1e-3) / 1e9
             roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                        "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_kind,
+                        "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_source,
+                        "peak_source": peak_kind,
                         "us_per_launch": kms / kcount * 1e3, "launches_per_step": kcount / args.steps,
                         "algorithmic_bytes_per_launch": kbytes}
         total_edges = n_edges * world
         b_alg = algorithmic_bytes(n, n_edges, wl)
         step_s = t_dev / args.steps
+        config = workload_config(args.workload, wl, world)
+        config.update({
+            "edges_per_gpu": n_edges,
+            "l2": "256 MiB memset between steps (untimed)",
+            "launch": "eager" if graph is None else ("cuda-graph replay of the step's kernels" +
+                                                      (" + the NCCL all-reduce" if graph_has_collective else "")),
+            "collective": "loss all-reduce (NCCL)" if world > 1 else "none",
+            "numa_node": numa_node, "pci_bus": pci_bus})
         line = {
-            "metric": "edges/s: graph-build + 4-layer MPNN fwd", "value": total_edges * args.steps / t_dev,
+            "metric": metric_name(wl), "value": total_edges * args.steps / t_dev,
             "unit": "edges/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (graph build in f64)", "data": "synthetic",
-            "config": {"workload": args.workload, "points_per_gpu": n, "edges_per_gpu": n_edges,
-                       "frames_per_gpu": n_frames, "k": wl["k"], "layers": wl["layers"], "channels": wl["channels"],
-                       "edge_attr": "relative_position (De=2)", "aggr": "max", "parallelism": f"dp{world} (frames)",
-                       "l2": "256 MiB memset between steps (untimed)", "launch": "eager" if graph is None else "cuda-graph replay of the step's kernels", "collective": "loss all-reduce (NCCL)" if world > 1 else "none"},
-            "e2e": {"value": total_edges * e2e_steps / t_e2e, "unit": "edges/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / e2e_steps * 1e3,
-                    "api": "rgnn_pipeline_forward_host (pinned host buffers)"},
+            "config": config,
+            "e2e": e2e["e2e"], "e2e_embeddings_only": e2e["e2e_embeddings_only"],
             "gpu_launches": int(launches),
             "roofline": roofline,
             "path_roofline": {"algorithmic_bytes_per_step": b_alg, "achieved": b_alg / step_s / 1e9, "peak": peak_gbs,
@@ -441,7 +572,7 @@ def main_gpu(args, wl):
             "clocks": clocks, "loss": loss_value,
         }
         if world == 1 and not args.no_cpu_baseline:
-            base = run_cpu_baseline(wl, steps=6, warmup=1)
+            base = run_cpu_baseline(wl, steps=4, warmup=1)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -459,6 +590,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-graph-collective", action="store_true", help="keep the NCCL all-reduce out of the CUDA graph (N > 1)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -274,6 +274,12 @@ typedef struct rgnn_pipeline_desc {
   const float* const* bn_weight;  /* HOST array of device pointers [n_layers], entries may be NULL */
   const float* const* bn_bias;
   float bn_eps;
+  /* Optional running statistics (torch BatchNorm1d semantics: running = (1 - momentum) * running +
+   * momentum * batch, unbiased variance), updated in place by every forward when non-NULL: HOST arrays of
+   * device pointers [n_layers], the arrays themselves or single entries may be NULL. */
+  float bn_momentum;
+  float* const* bn_running_mean;
+  float* const* bn_running_var;
 } rgnn_pipeline_desc;
 
 size_t rgnn_pipeline_workspace_bytes(const rgnn_pipeline_desc* desc, int64_t n_points,

@@ -159,3 +159,21 @@ def relative_error(actual: torch.Tensor, expected: torch.Tensor) -> float:
     a, e = actual.double(), expected.double()
     denom = e.abs().max().clamp(min=1e-30)
     return float((a - e).abs().max() / denom)
+
+
+def rowwise_relative_error(actual: torch.Tensor, expected: torch.Tensor) -> float:
+    """Element-wise companion of ``relative_error``: max over all elements of
+    |a - e| / max(|e_row|), every node's row measured against ITS OWN scale (a node whose
+    embedding is small must be as accurate, relatively, as the largest one)."""
+    a, e = actual.double(), expected.double()
+    scale = e.abs().amax(dim=1, keepdim=True).clamp(min=1e-30)
+    return float(((a - e).abs() / scale).max())
+
+
+def parity_report(actual: torch.Tensor, expected: torch.Tensor) -> Dict[str, float]:
+    """Both metrics plus the fraction of elements off by more than 1e-4 of their row scale."""
+    a, e = actual.double(), expected.double()
+    scale = e.abs().amax(dim=1, keepdim=True).clamp(min=1e-30)
+    rel = (a - e).abs() / scale
+    return {"max_norm": relative_error(actual, expected), "rowwise": float(rel.max()),
+            "frac_above_1e-4": float((rel > 1e-4).double().mean())}

@@ -57,7 +57,8 @@ class PipelineDesc(C.Structure):
         ("edge_mode", C.c_int32), ("n_edge_features", C.c_int32),
         ("edge_features", C.c_int32 * MAX_EDGE_FEATURES), ("n_layers", C.c_int32),
         ("layers", C.POINTER(ConvDesc)), ("bn_weight", C.POINTER(C.c_void_p)),
-        ("bn_bias", C.POINTER(C.c_void_p)), ("bn_eps", C.c_float),
+        ("bn_bias", C.POINTER(C.c_void_p)), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+        ("bn_running_mean", C.POINTER(C.c_void_p)), ("bn_running_var", C.POINTER(C.c_void_p)),
     ]
 
 

@@ -246,12 +246,15 @@ static int pipeline_forward_impl(const rgnn_pipeline_desc* desc, const float* po
     float* st = w.stats + static_cast<size_t>(l) * 3 * c_max;
     const float* bw = desc->bn_weight != nullptr ? desc->bn_weight[l] : nullptr;
     const float* bb = desc->bn_bias != nullptr ? desc->bn_bias[l] : nullptr;
+    float* rmean = desc->bn_running_mean != nullptr ? desc->bn_running_mean[l] : nullptr;
+    float* rvar = desc->bn_running_var != nullptr ? desc->bn_running_var[l] : nullptr;
+    if (rmean == nullptr || rvar == nullptr) rmean = rvar = nullptr;
     if (fused_partials > 0) {
       // the node-update contraction already produced the per-tile column sums
-      RGNN_RETURN_IF_ERROR(bn_finalize_partials(cw.bn_partial, fused_partials, n, s.c_out, bw, bb, desc->bn_eps, 0.f,
-                                                nullptr, nullptr, st, st + c_max, st + 2 * c_max, stream));
+      RGNN_RETURN_IF_ERROR(bn_finalize_partials(cw.bn_partial, fused_partials, n, s.c_out, bw, bb, desc->bn_eps,
+                                                desc->bn_momentum, rmean, rvar, st, st + c_max, st + 2 * c_max, stream));
     } else {
-      RGNN_RETURN_IF_ERROR(bn_statistics(out, s.c_out, n, s.c_out, bw, bb, desc->bn_eps, 0.f, nullptr, nullptr,
+      RGNN_RETURN_IF_ERROR(bn_statistics(out, s.c_out, n, s.c_out, bw, bb, desc->bn_eps, desc->bn_momentum, rmean, rvar,
                                          st, st + c_max, st + 2 * c_max, w.bn_scratch, stream));
     }
     in.x = out; in.ldx = s.c_out; in.rows = nullptr;
@@ -361,6 +364,8 @@ int rgnn_pipeline_forward_host(const rgnn_pipeline_desc* desc, const float* pos_
   hash_bytes(key, desc->layers, sizeof(rgnn_conv_desc) * desc->n_layers);
   if (desc->bn_weight != nullptr) hash_bytes(key, desc->bn_weight, sizeof(float*) * desc->n_layers);
   if (desc->bn_bias != nullptr) hash_bytes(key, desc->bn_bias, sizeof(float*) * desc->n_layers);
+  if (desc->bn_running_mean != nullptr) hash_bytes(key, desc->bn_running_mean, sizeof(float*) * desc->n_layers);
+  if (desc->bn_running_var != nullptr) hash_bytes(key, desc->bn_running_var, sizeof(float*) * desc->n_layers);
   hash_bytes(key, frame_ptr_host, sizeof(int64_t) * (n_frames + 1));
   const void* ptrs[] = {pos_host, vel_host, x0_host, edge_index_host, edge_attr_host, h_host, workspace};
   hash_bytes(key, ptrs, sizeof(ptrs));

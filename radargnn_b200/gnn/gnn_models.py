@@ -144,8 +144,18 @@ class DetNetBasic(torch.nn.Module):
             raise NotImplementedError("the fused path starts at the conv stack: run the embedding MLPs first")
         layers = [conv.conv_params() for conv in self.convs]
         bn = [(b.module.weight, b.module.bias) for b in self.batch_norms]
+        # The fused kernels normalise with BATCH statistics (the reference never leaves training mode,
+        # SURVEY.md section 5).  A BatchNorm in eval mode would silently give other numbers than forward():
+        if any(not b.module.training and b.module.running_mean is not None for b in self.batch_norms):
+            raise RuntimeError("forward_from_points normalises with batch statistics (training-mode BatchNorm, as the "
+                               "reference always runs it); call model.train() or use forward() for eval-mode BatchNorm")
+        running = [(b.module.running_mean, b.module.running_var) for b in self.batch_norms]
+        momenta = {0.1 if b.module.momentum is None else float(b.module.momentum) for b in self.batch_norms}
+        if len(momenta) != 1:
+            raise ValueError("the fused path takes one BatchNorm momentum for the whole stack")
         return ops.PipelineConfig(
-            layers=layers, bn=bn, algorithm=graph_config.graph_construction_algorithm,
+            layers=layers, bn=bn, bn_running=running, bn_momentum=momenta.pop(),
+            algorithm=graph_config.graph_construction_algorithm,
             k=graph_config.k if graph_config.k is not None else 6,
             r=graph_config.r if graph_config.r is not None else 1.0,
             distance_definition=graph_config.distance_definition, edge_features=list(graph_config.edge_features),
@@ -157,7 +167,16 @@ class DetNetBasic(torch.nn.Module):
         ``pos`` / ``vel`` float32 ``[N, 2]``, ``x`` float32 ``[N, C0]``, ``frame_ptr`` ``[F + 1]`` point
         offsets of the frames of the batch.  Returns ``(edge_index, edge_attr, h)`` or, with heads,
         ``(edge_index, edge_attr, c, bb)``."""
+        if pos.dtype == torch.float64 or vel.dtype == torch.float64:
+            # input contract of the fused call: float32 coordinates (create_graph_data's pos / vel dtype,
+            # dataset_creation.py:810-811); fp64 point clouds go through GraphConstructor, which searches in fp64
+            if not (torch.equal(pos.float().double(), pos.double()) and torch.equal(vel.float().double(), vel.double())):
+                raise ValueError("forward_from_points takes float32 coordinates; these float64 values are not "
+                                 "float32-representable, so neighbours / edge_attr could differ from GraphConstructor's")
         edge_index, edge_attr, h = ops.pipeline_forward(self.pipeline_config(graph_config), pos, vel, x, frame_ptr)
+        for b in self.batch_norms:   # torch.nn.BatchNorm1d bookkeeping of a training-mode forward
+            if b.module.num_batches_tracked is not None:
+                b.module.num_batches_tracked += 1
         if not heads:
             return edge_index, edge_attr, h
         return edge_index, edge_attr, _run_mlp(self.classification_head, h), _run_mlp(self.regression_head, h)

@@ -371,6 +371,9 @@ class PipelineConfig:
     edge_features: Sequence[str] = ("relative_position",)
     edge_mode: str = "directed"
     bn_eps: float = 1e-5
+    # optional running statistics per layer, updated in place by every forward (torch BatchNorm1d semantics)
+    bn_running: Optional[List[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]]] = None
+    bn_momentum: float = 0.1
 
 
 class _PipelineHandle:
@@ -406,6 +409,20 @@ class _PipelineHandle:
         d.bn_weight = C.cast(self.bn_w, C.POINTER(C.c_void_p))
         d.bn_bias = C.cast(self.bn_b, C.POINTER(C.c_void_p))
         d.bn_eps = float(cfg.bn_eps)
+        d.bn_momentum = float(cfg.bn_momentum)
+        if cfg.bn_running is not None:
+            self.bn_rm = (C.c_void_p * n_layers)()
+            self.bn_rv = (C.c_void_p * n_layers)()
+            for i, (rm, rv) in enumerate(cfg.bn_running):
+                if rm is None or rv is None:
+                    continue
+                if rm.dtype != torch.float32 or rv.dtype != torch.float32 or not rm.is_cuda or not rv.is_cuda \
+                        or not rm.is_contiguous() or not rv.is_contiguous():
+                    raise ValueError("running statistics must be contiguous float32 CUDA tensors (they are updated in place)")
+                self.keep += [rm, rv]
+                self.bn_rm[i], self.bn_rv[i] = rm.data_ptr(), rv.data_ptr()
+            d.bn_running_mean = C.cast(self.bn_rm, C.POINTER(C.c_void_p))
+            d.bn_running_var = C.cast(self.bn_rv, C.POINTER(C.c_void_p))
         self.desc = d
         self.edge_dim = _lib.load().rgnn_edge_feature_width(_lib.int32_array(ids), len(ids))
 

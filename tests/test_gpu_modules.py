@@ -248,8 +248,24 @@ def test_detnet_fused_path_equals_layerwise(gnn):
     x = torch.randn(X.shape[0], 8, device=DEV)
     ei, ea, c, bb = model.forward_from_points(gcfg, pos, vel, x, ptr)
     np.testing.assert_array_equal(ei.cpu().numpy().T, go.batched_edges([f.X_cc for f in frames], "knn", k=8))
+    # the fused path updated the running statistics like one training-mode forward() does
+    rm1 = [b.module.running_mean.clone() for b in model.batch_norms]
+    rv1 = [b.module.running_var.clone() for b in model.batch_norms]
+    assert all(int(b.module.num_batches_tracked) == 1 for b in model.batch_norms)
+    for b in model.batch_norms:
+        b.module.reset_running_stats()
     c2, bb2 = model(x, ei, ea)
     assert mo.relative_error(c, c2) <= 1e-5 and mo.relative_error(bb, bb2) <= 1e-5
+    for b, rm, rv in zip(model.batch_norms, rm1, rv1):
+        torch.testing.assert_close(b.module.running_mean, rm, rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(b.module.running_var, rv, rtol=1e-4, atol=1e-6)
+    # eval-mode BatchNorm would use other statistics than the fused kernels: refused, not silently different
+    model.eval()
+    with pytest.raises(RuntimeError, match="batch statistics"):
+        model.forward_from_points(gcfg, pos, vel, x, ptr)
+    model.train()
+    with pytest.raises(ValueError, match="float32-representable"):
+        model.forward_from_points(gcfg, pos.double() + 1e-9, vel.double(), x, ptr)
 
 
 def test_cpu_tensors_are_rejected(gnn):
