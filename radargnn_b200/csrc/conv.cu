@@ -25,18 +25,6 @@ namespace {
 
 constexpr int kAggThreads = 256;
 
-// what a node without incoming edge contributes on the folded tensor-core path (null w_t: nothing)
-struct IsolatedNodeTerm {
-  const float* w_t = nullptr;  // W_pre[:, 0:C], row stride ldw
-  int64_t ldw = 0;
-  const float* x = nullptr;    // layer input rows
-  int64_t ldx = 0;
-  const int32_t* rows = nullptr;
-  int32_t c = 0;
-  const float* mean = nullptr; const float* scale = nullptr; const float* beta = nullptr;
-  int32_t relu = 0;
-};
-
 // W_e (row-major [p, ldw], rows = output channels) -> shared [de][pp], zero padded
 __device__ __forceinline__ void stage_edge_weights(const float* __restrict__ w_e, int64_t ldw, int p, int pp,
                                                    int de, float* __restrict__ smem) {

@@ -51,6 +51,45 @@ struct ConvWorkspace {
   int32_t* tc_status;    // device flag
 };
 
+// what a node without incoming edge contributes on the folded tensor-core path (null w_t: nothing)
+struct IsolatedNodeTerm {
+  const float* w_t = nullptr;  // W_pre[:, 0:C], row stride ldw
+  int64_t ldw = 0;
+  const float* x = nullptr;    // layer input rows
+  int64_t ldx = 0;
+  const int32_t* rows = nullptr;
+  int32_t c = 0;
+  const float* mean = nullptr; const float* scale = nullptr; const float* beta = nullptr;
+  int32_t relu = 0;
+};
+
+// Fused edge aggregate + node update (fused_layer.cu): the segmented reduce over the CSC view writes the
+// aggregated messages M' of a 128-row tile straight into shared memory, from where they feed the tcgen05
+// update contraction -- M' never exists in HBM.  Split layout only (C = 64 MPNNConv, max / min / mean).
+struct FusedLayerArgs {
+  // aggregate side (what launch_edge_aggregate_split takes)
+  int32_t aggr = 0;
+  const float* bm = nullptr; const float* bt = nullptr;   // B main [N, 128], B tail [N, 4]
+  int32_t p = 0, de = 0;
+  const float* bias_msg = nullptr; const float* w_e = nullptr; int64_t ldwe = 0;
+  const float* ea = nullptr; const int32_t* csc_ptr = nullptr; const int32_t* csc_src = nullptr;
+  IsolatedNodeTerm iso;
+  // update side
+  const float* x = nullptr; int64_t ldx = 0; const int32_t* x_rows = nullptr;   // layer input [N, 64] (optional gather map)
+  const float* x_mean = nullptr; const float* x_scale = nullptr; const float* x_beta = nullptr; int32_t relu_x = 0;
+  const float* wpack = nullptr;          // tc_pack_weights image of the update weights: K blocks [x | M' main | tail]
+  const float* w_tail = nullptr; int64_t ld_wtail = 0;   // update weights of the tail channels: post_weight[:, C + 128 ...]
+  const float* bias_post = nullptr;
+  int32_t c_out = 0;
+  float* y = nullptr; int64_t ldy = 0;
+  double* bn_partial = nullptr;          // [2][c_out][partials] column sums / squares, one partial per CTA, or null
+  int32_t* status = nullptr;
+  int64_t n_nodes = 0;
+};
+bool fused_layer_supported(const rgnn_conv_desc& d, const ConvShape& s);
+int64_t fused_layer_partials();          // partial sums per channel the kernel writes (= CTAs launched)
+int launch_fused_layer(const FusedLayerArgs& a, cudaStream_t stream);
+
 // shapes of the two node contractions of a layer when they run on the tensor cores
 inline TcGemmShape conv_pre_shape(const ConvShape& s) { TcGemmShape t; t.k1 = s.c; t.n = s.p; return t; }
 inline TcGemmShape conv_post_shape(const rgnn_conv_desc& d, const ConvShape& s) {

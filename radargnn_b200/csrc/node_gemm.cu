@@ -23,103 +23,12 @@
 #include <string.h>
 
 #include "node_gemm.cuh"
+#include "tc_common.cuh"
 
 namespace rgnn {
 namespace {
 
-constexpr int kRows = 128;     // UMMA M
-constexpr int kKc = 32;        // floats of K per chunk (4 MMA k-steps of 8)
-constexpr int kABufFloats = kRows * kKc;  // one hi or lo image of a chunk
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor).  The operand is
-// stored as panels of [rows x 128 bytes] (32 floats of K): row r of an 8-row group sits at r * 128
-// bytes and its 16-byte chunk c at position c ^ (r % 8) (Swizzle<3,4,3>, what TMA's 128B swizzle
-// writes); 8-row groups are SBO = 1024 bytes apart; LBO is unused for swizzled K-major operands.
-// A k-step (8 floats = 32 bytes) is selected by advancing the start address by 32 bytes.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
-  d |= static_cast<uint64_t>(1) << 16;            // LBO (ignored)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;    // SBO
-  d |= static_cast<uint64_t>(1) << 46;            // descriptor version 1 (Blackwell)
-  d |= static_cast<uint64_t>(2) << 61;            // layout_type SWIZZLE_128B
-  return d;
-}
-
-// float offset of (row, 16-byte chunk c of the 32-float K block) inside one swizzled panel
-__host__ __device__ __forceinline__ int sw128_offset(int row, int chunk) {
-  return (row >> 3) * 256 + (row & 7) * 32 + ((chunk ^ (row & 7)) << 2);
-}
-
-// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, A and B K-major
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(m >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t leader) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-      "}\n" ::"r"(smem_u32(bar)), "r"(leader)
-      : "memory");
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-
-// Bounded wait: a lost arrival must not hang the GPU (returns false on timeout).  try_wait carries a
-// suspend-time hint: the warp sleeps in hardware until the phase completes (it is woken by the arrival) or
-// the hint expires, instead of re-issuing the poll -- with ~20 warps parked on barriers at any time, hot
-// polling took the issue slots of the few warps that had work (every role ran at ~15 cycles/instruction).
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  for (int it = 0; it < (1 << 18); ++it) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(20000u)
-        : "memory");
-    if (done) return true;
-  }
-  return false;
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-  lo = v - hi;  // exact
-}
+using namespace tc;   // kRows, kKc, kABufFloats and the inline-PTX helpers (tc_common.cuh)
 
 // ---- weight packing ------------------------------------------------------------------------
 // image = per 32-float K block one swizzled [np x 32] panel of hi parts directly followed by the panel of
@@ -237,42 +146,6 @@ __device__ __forceinline__ SmemLayout carve_smem(unsigned char* base, int np, in
   s.bar = reinterpret_cast<uint64_t*>(f); f += 2 * kBarCount;
   s.tmem_base = reinterpret_cast<uint32_t*>(f);
   return s;
-}
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-
-// arrive on `bar` once every cp.async this thread has issued so far has landed (counts as one of the
-// barrier's expected arrivals)
-__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// 16 consecutive TMEM columns of this thread's lane (lane = 32 * (warp % 4) + lane id)
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
-      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
-        "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
-      : "memory");
-}
-
-// D[tmem] (+)= A[tmem] . B[smem]^T
-__device__ __forceinline__ void umma_tf32_ts_pred(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                                  uint32_t accumulate, uint32_t leader) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
-      : "memory");
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)

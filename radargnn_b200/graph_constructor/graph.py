@@ -172,8 +172,11 @@ class GeometricGraph(Graph):
         """Node feature matrix ``X_feat`` [N, Fn], columns in list order (reference graph.py:225-275)."""
         dev = _device()
         n = np.asarray(self.X).shape[0]
-        if np.asarray(self.X).ndim != 2 or np.asarray(self.X).shape[1] != 2 or np.asarray(self.V).shape != np.asarray(self.X).shape:
-            raise ValueError("X and V must both be [N, 2] arrays (the node-feature kernel reads two columns each)")
+        # the node-feature kernel reads exactly two columns of X / V: check the ones the request needs
+        for arr, label, users in ((self.X, "X", ("spatial_coordinates",)),
+                                  (self.V, "V", ("velocity_vector", "velocity_vector_length"))):
+            if any(f in users for f in features) and (arr is None or np.asarray(arr).ndim != 2 or np.asarray(arr).shape != (n, 2)):
+                raise ValueError(f"{label} must be an [N, 2] array for the node features {users}")
         names = ("rcs", "time_index", "degree", "velocity_vector_length", "velocity_vector", "spatial_coordinates")
         known = []
         for f in features:
