@@ -756,6 +756,19 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
       iso.w_t = d.pre_weight[0]; iso.ldw = s.p; iso.x = in.x; iso.ldx = in.ldx; iso.c = s.c; iso.rows = in.rows;
       iso.mean = in.mean; iso.scale = in.scale; iso.beta = in.beta; iso.relu = in.relu;
     }
+    if (fused_layer_supported(d, s)) {
+      // aggregate + node update in one kernel: M' stays in shared / tensor memory (fused_layer.cu)
+      FusedLayerArgs f;
+      f.aggr = d.aggr; f.bm = w.b; f.bt = w.bt; f.p = s.p; f.de = s.de;
+      f.bias_msg = bias; f.w_e = w_e; f.ldwe = ldwe; f.ea = ea; f.csc_ptr = csc_ptr; f.csc_src = csc_src; f.iso = iso;
+      f.x = in.x; f.ldx = in.ldx; f.x_rows = in.rows;
+      f.x_mean = in.mean; f.x_scale = in.scale; f.x_beta = in.beta; f.relu_x = in.relu;
+      f.wpack = wpack_post; f.w_tail = d.post_weight[0] + s.c + s.pm; f.ld_wtail = s.c + s.p;
+      f.bias_post = d.post_bias[0]; f.c_out = s.c_out; f.y = out; f.ldy = s.c_out; f.n_nodes = n_nodes;
+      f.status = w.tc_status;
+      if (bn_partials != nullptr) { f.bn_partial = w.bn_partial; *bn_partials = fused_layer_partials(n_nodes); }
+      return launch_fused_layer(f, stream);
+    }
     if (s.split) {
       RGNN_RETURN_IF_ERROR(launch_edge_aggregate_split(d.aggr, w.b, w.bt, s, bias, w_e, ldwe, ea, csc_ptr, csc_src, n_nodes,
                                                        w.m, w.mt, stream, iso));

@@ -87,7 +87,7 @@ struct FusedLayerArgs {
   int64_t n_nodes = 0;
 };
 bool fused_layer_supported(const rgnn_conv_desc& d, const ConvShape& s);
-int64_t fused_layer_partials();          // partial sums per channel the kernel writes (= CTAs launched)
+int64_t fused_layer_partials(int64_t n_nodes);   // partial sums per channel the kernel writes (= CTAs launched, <= SM count)
 int launch_fused_layer(const FusedLayerArgs& a, cudaStream_t stream);
 
 // shapes of the two node contractions of a layer when they run on the tensor cores
@@ -134,7 +134,8 @@ inline ConvWorkspace carve_conv_workspace(ArenaT& a, const rgnn_conv_desc& d, co
     w.wpack_pre = a.template take<float>(tc_pack_floats(conv_pre_shape(s)));
     w.wpack_post = a.template take<float>(tc_pack_floats(conv_post_shape(d, s)));
     w.w_fold = a.template take<float>(static_cast<size_t>(s.c_out) * s.c);
-    w.bn_partial = a.template take<double>(static_cast<size_t>(tc_tiles(n_nodes)) * 2 * s.c_out);
+    // one partial per 128-row tile (node_gemm.cu) or per CTA (fused_layer.cu, at most one per SM)
+    w.bn_partial = a.template take<double>(static_cast<size_t>(tc_tiles(n_nodes) + sm_count()) * 2 * s.c_out);
     w.tc_status = a.template take<int32_t>(64);
   }
   return w;
