@@ -759,7 +759,7 @@ int conv_forward(const rgnn_conv_desc& d, const ConvShape& s, const ConvInput& i
     if (fused_layer_supported(d, s)) {
       // aggregate + node update in one kernel: M' stays in shared / tensor memory (fused_layer.cu)
       FusedLayerArgs f;
-      f.aggr = d.aggr; f.bm = w.b; f.bt = w.bt; f.p = s.p; f.de = s.de;
+      f.aggr = d.aggr; f.bm = w.b; f.bt = w.bt; f.mt = w.mt; f.p = s.p; f.de = s.de;
       f.bias_msg = bias; f.w_e = w_e; f.ldwe = ldwe; f.ea = ea; f.csc_ptr = csc_ptr; f.csc_src = csc_src; f.iso = iso;
       f.x = in.x; f.ldx = in.ldx; f.x_rows = in.rows;
       f.x_mean = in.mean; f.x_scale = in.scale; f.x_beta = in.beta; f.relu_x = in.relu;

@@ -70,6 +70,7 @@ struct FusedLayerArgs {
   // aggregate side (what launch_edge_aggregate_split takes)
   int32_t aggr = 0;
   const float* bm = nullptr; const float* bt = nullptr;   // B main [N, 128], B tail [N, 4]
+  float* mt = nullptr;                                    // scratch [N, 4]: tail channels of M' (reduced before the fused kernel)
   int32_t p = 0, de = 0;
   const float* bias_msg = nullptr; const float* w_e = nullptr; int64_t ldwe = 0;
   const float* ea = nullptr; const int32_t* csc_ptr = nullptr; const int32_t* csc_src = nullptr;

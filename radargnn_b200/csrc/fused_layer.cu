@@ -59,7 +59,7 @@ constexpr int kAggRegs = 144, kTileRegs = 80;
 constexpr uint32_t kXCol = 128, kMCol = 256;                // TMEM columns: accumulator 0.., x stages, M' stages
 
 struct FusedParams {
-  const float* bm; const float* bt; int32_t p;
+  const float* bm; const float* mt; int32_t p;   // B main [N, 128]; reduced tail channels of M' [N, 4]
   const float* bias_msg; const float* w_e; int64_t ldwe; const float* ea;
   const int32_t* csc_ptr; const int32_t* csc_src;
   IsolatedNodeTerm iso;
@@ -71,6 +71,7 @@ struct FusedParams {
   double* bn_partial; int32_t n_partials;
   int32_t* status;
   int32_t n_nodes, rows_per_cta, tiles_per_cta;
+  long long* trace; int32_t trace_cta;   // debug timeline of one CTA (scripts/trace_fused.py)
 };
 
 struct FusedSmem {
@@ -79,8 +80,6 @@ struct FusedSmem {
   float* stage;    // [4 tile warps][32][36]
   float* ws;       // [DE][kMain] edge weights of the main channels, transposed
   float* bs;       // [kMain] message bias
-  float* wte;      // [4 attributes][4 tail channels] edge weights of the tail channels
-  float* bte;      // [4] message bias of the tail channels
   float* wtail;    // [4 tail channels][64] update weights of the tail channels
   float* bias;     // [64] update bias
   float* bn;       // [3][64] BatchNorm-on-load of x
@@ -93,7 +92,7 @@ struct FusedSmem {
 
 __host__ __device__ inline size_t fused_smem_floats(int np, int de) {
   return static_cast<size_t>(kKBlocks) * 2 * np * 32 + kRing * kQuarterFloats + 4 * kStageFloats + de * kMain + kMain +
-         16 + 4 + 4 * 64 + 64 + 3 * 64 + 2 * 4 * 64 + 2 * (2 * kRing + 2) + kRing + 4;
+         4 * 64 + 64 + 3 * 64 + 2 * 4 * 64 + 2 * (2 * kRing + 2) + kRing + 4;
 }
 
 __device__ __forceinline__ FusedSmem carve_fused(unsigned char* base, int np, int de) {
@@ -104,8 +103,6 @@ __device__ __forceinline__ FusedSmem carve_fused(unsigned char* base, int np, in
   s.stage = f; f += 4 * kStageFloats;
   s.ws = f; f += de * kMain;
   s.bs = f; f += kMain;
-  s.wte = f; f += 16;
-  s.bte = f; f += 4;
   s.wtail = f; f += 4 * 64;
   s.bias = f; f += 64;
   s.bn = f; f += 3 * 64;
@@ -202,11 +199,6 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
     s.ws[i] = p.w_e[static_cast<int64_t>(ch) * p.ldwe + d];
   }
   for (int i = tid; i < kMain; i += kFusedThreads) s.bs[i] = p.bias_msg[i];
-  if (tid < 16) {
-    const int d = tid >> 2, j = tid & 3;
-    s.wte[tid] = (d < DE && kMain + j < p.p) ? p.w_e[static_cast<int64_t>(kMain + j) * p.ldwe + d] : 0.f;
-  }
-  if (tid < 4) s.bte[tid] = kMain + tid < p.p ? p.bias_msg[kMain + tid] : 0.f;
   for (int i = tid; i < 4 * 64; i += kFusedThreads) {
     const int j = i >> 6, n = i & 63;
     s.wtail[i] = (kMain + j < p.p && n < p.c_out) ? p.w_tail[static_cast<int64_t>(n) * p.ld_wtail + j] : 0.f;
@@ -230,6 +222,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *s.tmem_base;
 
+  if (p.trace != nullptr && blockIdx.x == p.trace_cta && tid == 0) p.trace[1000] = clock64();
   const int row_begin = blockIdx.x * p.rows_per_cta;
   const int row_end = min(p.n_nodes, row_begin + p.rows_per_cta);
   const int tiles = p.tiles_per_cta;
@@ -279,6 +272,8 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
 
     for (int it = 0; it < kPasses; ++it) {
       const int unit = warp + it * kAggWarps;
+      long long* tr = (p.trace != nullptr && blockIdx.x == p.trace_cta && lane == 0 && it < 24) ? p.trace + 64 + warp * 48 + it * 2 : nullptr;
+      if (tr != nullptr) tr[0] = clock64();
       const int row = row_base + it * kPassRows;
       const bool live = row < row_end;
       load_ptr(it + 2, beg2, deg2);
@@ -348,10 +343,11 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
       for (int i = 0; i < 4; ++i) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // torch_scatter: empty segments aggregate to 0
       if (live) {
         if (deg_row > 0) {
+          const float inv = 1.f / static_cast<float>(deg_row);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 bmain = ld4(&s.bs[32 * i + 4 * q]);
-            if (MODE == RGNN_AGGR_MEAN) r[i] = fma4(1.f / static_cast<float>(deg_row), acc[i], bmain);
+            if (MODE == RGNN_AGGR_MEAN) r[i] = fma4(inv, acc[i], bmain);
             else r[i] = add4(bmain, acc[i]);
           }
         } else if (p.iso.w_t != nullptr) {
@@ -379,7 +375,9 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
       }
       // the unit's four rows -> ring quarter (unit / 8) % kRing, once the tile warp has drained its previous use
       const int qi = unit >> 3, slot = qi & (kRing - 1), round = qi / kRing;
+      const long long tw = tr != nullptr ? clock64() : 0;
       if (round >= 1 && !wait_consumed(&s.consumed[slot], round)) timed_out = true;
+      if (tr != nullptr) tr[1] = clock64() - tw;
       const int rq = (4 * unit + quarter) & 31;
       float* dst = s.ring + slot * kQuarterFloats + rq * 32 + ((q ^ (rq & 7)) << 2);
 #pragma unroll
@@ -408,13 +406,38 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
     float* st = s.stage + qd * kStageFloats;
     const int n_blocks = np >> 4;
     double bn_sum = 0.0, bn_sq = 0.0;             // thread tt < c_out: running column sums of channel tt
+
+    // the x rows of a tile are pulled into L2 two tiles ahead (a row = two 128-byte lines), so that the loads of
+    // step (1) are L2 hits: a shared-memory staging buffer would take 32 KB away from the L1 the gathers live on
+    auto prefetch_x = [&](int t) {
+      const int row = row_begin + t * kRows + tt;
+      if (t < tiles && row < row_end) {
+        const float* xr = p.x + (p.x_rows != nullptr ? static_cast<int64_t>(p.x_rows[row]) : row) * p.ldx;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(xr));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + 32));
+      }
+    };
+    prefetch_x(0);
+    prefetch_x(1);
+
+    // Tail channels of M' (the De edge-attribute columns of the message): reduced per row by tail_reduce_kernel
+    // (below) before this kernel starts -- a per-row gather in the tile warps costs four dependent load rounds
+    // of ~3 k cycles each behind the aggregate warps' gathers in the load-store queue.  One 16-byte load here,
+    // fetched one tile ahead.
     const int pt = p.p - kMain;                   // tail channels (1..4)
+    auto load_tail = [&](int t) {
+      const int row = row_begin + t * kRows + tt;
+      return (t < tiles && row < row_end) ? ld4(p.mt + static_cast<int64_t>(row) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 mt4 = load_tail(0);
 
     for (int t = 0; t < tiles; ++t) {
       const int row = row_begin + t * kRows + tt;
       const bool row_ok = row < row_end;
       const uint32_t par = static_cast<uint32_t>(t) & 1u;
-      // ---- (1) x row -> BatchNorm + ReLU on load -> hi / lo -> TMEM ----
+      long long* tr = (p.trace != nullptr && blockIdx.x == p.trace_cta && tt == 0 && t < 8) ? p.trace + t * 8 : nullptr;
+      if (tr != nullptr) tr[0] = clock64();
+      // ---- (1) x row (L2-prefetched) -> BatchNorm + ReLU of the previous layer -> hi / lo -> TMEM ----
       {
         const float* xr = p.x + (row_ok ? (p.x_rows != nullptr ? static_cast<int64_t>(p.x_rows[row]) : row) : 0) * p.ldx;
 #pragma unroll 1
@@ -438,64 +461,12 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
           store_panel_hi_lo(lane_base + kXCol + pn * 64, v);
         }
       }
-      // ---- (2) tail channels of M' for this row: gather + reduce over the row's slots, 8 at a time ----
-      float mt[4] = {0.f, 0.f, 0.f, 0.f};
-      {
-        constexpr float kInit = MODE == RGNN_AGGR_MAX ? -INFINITY : (MODE == RGNN_AGGR_MIN ? INFINITY : 0.f);
-        int beg = 0, deg = 0;
-        if (row_ok) { beg = p.csc_ptr[row]; deg = p.csc_ptr[row + 1] - beg; }
-        float4 tacc = make_float4(kInit, kInit, kInit, kInit);
-        float4 we[DE];
-#pragma unroll
-        for (int d = 0; d < DE; ++d) we[d] = ld4(s.wte + 4 * d);
-        for (int b = 0; b < deg; b += 8) {
-          int src[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) src[j] = b + j < deg ? p.csc_src[beg + b + j] : 0;
-          float4 tv[8];
-          float ev[8][DE];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const bool on = b + j < deg;
-            tv[j] = on ? ld4(p.bt + static_cast<int64_t>(src[j]) * 4) : tacc;
-#pragma unroll
-            for (int d = 0; d < DE; ++d) ev[j][d] = on ? p.ea[static_cast<int64_t>(beg + b + j) * DE + d] : 0.f;
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (b + j < deg) {
-              float4 tj = tv[j];
-#pragma unroll
-              for (int d = 0; d < DE; ++d) tj = fma4(ev[j][d], we[d], tj);
-              tacc = combine4<MODE>(tacc, tj);
-            }
-          }
-        }
-        const float4 bte = ld4(s.bte);
-        if (deg > 0) {
-          if (MODE == RGNN_AGGR_MEAN) {
-            const float inv = 1.f / static_cast<float>(deg);
-            mt[0] = fmaf(tacc.x, inv, bte.x); mt[1] = fmaf(tacc.y, inv, bte.y); mt[2] = fmaf(tacc.z, inv, bte.z); mt[3] = fmaf(tacc.w, inv, bte.w);
-          } else {
-            mt[0] = bte.x + tacc.x; mt[1] = bte.y + tacc.y; mt[2] = bte.z + tacc.z; mt[3] = bte.w + tacc.w;
-          }
-        } else if (row_ok && p.iso.w_t != nullptr) {
-          const float* xr = p.iso.x + (p.iso.rows != nullptr ? static_cast<int64_t>(p.iso.rows[row]) : row) * p.iso.ldx;
-          float t4[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int c = 0; c < p.iso.c; ++c) {
-            float xv = xr[c];
-            if (p.iso.mean != nullptr) xv = (xv - p.iso.mean[c]) * p.iso.scale[c] + p.iso.beta[c];
-            if (p.iso.relu) xv = fmaxf(xv, 0.f);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j < pt) t4[j] = fmaf(p.iso.w_t[static_cast<int64_t>(kMain + j) * p.iso.ldw + c], xv, t4[j]);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) mt[j] = -t4[j];
-        }
-      }
+      prefetch_x(t + 2);
+      if (tr != nullptr) tr[1] = clock64();
       // ---- (3) M' quarter: ring -> hi / lo -> TMEM ----
+      if (tr != nullptr) tr[2] = clock64();
       if (!mbar_wait(&full[qd], par)) timed_out = true;
+      if (tr != nullptr) tr[3] = clock64();
       {
         const float* src = s.ring + qd * kQuarterFloats + lane * 32;
         const int sw = lane & 7;
@@ -512,6 +483,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(a_full);
+      if (tr != nullptr) tr[4] = clock64();
       // ---- (4) the tile's MMAs: [x | M'] (TMEM) . W^T (shared memory), issued by one lane of tile warp 0 ----
       if (qd == 0) {
         if (!mbar_wait(a_full, par)) timed_out = true;
@@ -530,8 +502,12 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
         }
         umma_commit_pred(acc_full, leader);
       }
+      const float mt[4] = {mt4.x, mt4.y, mt4.z, mt4.w};
+      mt4 = load_tail(t + 1);
       // ---- (5) epilogue ----
+      if (tr != nullptr) tr[5] = clock64();
       if (!mbar_wait(acc_full, par)) timed_out = true;
+      if (tr != nullptr) tr[6] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int tile_row0 = row_begin + t * kRows + qd * 32;
       const int rows_valid = max(0, min(32, row_end - tile_row0));
@@ -554,7 +530,8 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
             o.z += __uint_as_float(r[j4 * 4 + 2]) + __uint_as_float(r2[j4 * 4 + 2]);
             o.w += __uint_as_float(r[j4 * 4 + 3]) + __uint_as_float(r2[j4 * 4 + 3]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o = fma4(mt[j], ld4(s.wtail + j * 64 + col), o);
+            for (int j = 0; j < 4; ++j)
+              if (j < pt) o = fma4(mt[j], ld4(s.wtail + j * 64 + col), o);
             *reinterpret_cast<float4*>(strow + hb * 16 + j4 * 4) = o;
           }
         }
@@ -592,6 +569,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
         __syncwarp();
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // accumulator reads done before the next tile's MMAs
+      if (tr != nullptr) tr[7] = clock64();
       if (p.bn_partial != nullptr) {
         asm volatile("bar.sync 1, 128;" ::: "memory");   // the four quarters' column sums are in shared memory
         if (tt < p.c_out) {
@@ -616,9 +594,91 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (p.trace != nullptr && blockIdx.x == p.trace_cta && tid == 0) p.trace[1001] = clock64();
   if (warp == kAggWarps) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
+}
+
+
+// ---- tail channels of the aggregated messages ------------------------------------------------------------
+// M'_tail[n, 0:4] = b_tail + reduce over n's slots of (B_tail[src] + W_e,tail e)   (0 for an empty segment; the
+// isolated-node cancel term -W_t x_n on the folded path).  8 lanes per row, lane = slot (coalesced slot loads,
+// one 16-byte gather per lane), fixed-order butterfly: deterministic sums.  [N, 4] floats, 1.6 MB at the
+// headline size -- read back by the fused kernel's tile warps with one load per row.
+template <int MODE, int DE>
+__global__ void __launch_bounds__(256)
+tail_reduce_kernel(const float* __restrict__ bt, int p, const float* __restrict__ bias, const float* __restrict__ w_e,
+                   int64_t ldwe, const float* __restrict__ ea, const int32_t* __restrict__ csc_ptr,
+                   const int32_t* __restrict__ csc_src, int n_nodes, float* __restrict__ out_t, IsolatedNodeTerm iso) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = gid >> 3, q = threadIdx.x & 7;
+  const bool live = row < n_nodes;
+  constexpr float kInit = MODE == RGNN_AGGR_MAX ? -INFINITY : (MODE == RGNN_AGGR_MIN ? INFINITY : 0.f);
+  float4 we[DE];
+#pragma unroll
+  for (int d = 0; d < DE; ++d) {
+    we[d].x = w_e[static_cast<int64_t>(kMain) * ldwe + d];
+    we[d].y = kMain + 1 < p ? w_e[static_cast<int64_t>(kMain + 1) * ldwe + d] : 0.f;
+    we[d].z = kMain + 2 < p ? w_e[static_cast<int64_t>(kMain + 2) * ldwe + d] : 0.f;
+    we[d].w = kMain + 3 < p ? w_e[static_cast<int64_t>(kMain + 3) * ldwe + d] : 0.f;
+  }
+  int beg = 0, deg = 0;
+  if (live) { beg = csc_ptr[row]; deg = csc_ptr[row + 1] - beg; }
+  float4 tacc = make_float4(kInit, kInit, kInit, kInit);
+  for (int b = q; b < deg; b += 8) {
+    const int src = csc_src[beg + b];
+    float4 t = ld4(bt + static_cast<int64_t>(src) * 4);
+#pragma unroll
+    for (int d = 0; d < DE; ++d) t = fma4(ea[static_cast<int64_t>(beg + b) * DE + d], we[d], t);
+    tacc = combine4<MODE>(tacc, t);
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    float4 other;
+    other.x = __shfl_xor_sync(0xffffffffu, tacc.x, o); other.y = __shfl_xor_sync(0xffffffffu, tacc.y, o);
+    other.z = __shfl_xor_sync(0xffffffffu, tacc.z, o); other.w = __shfl_xor_sync(0xffffffffu, tacc.w, o);
+    tacc = combine4<MODE>(tacc, other);
+  }
+  if (!live || q != 0) return;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);   // torch_scatter: empty segments aggregate to 0
+  if (deg > 0) {
+    const float4 bte = make_float4(bias[kMain], kMain + 1 < p ? bias[kMain + 1] : 0.f, kMain + 2 < p ? bias[kMain + 2] : 0.f,
+                                   kMain + 3 < p ? bias[kMain + 3] : 0.f);
+    if (MODE == RGNN_AGGR_MEAN) r = fma4(1.f / static_cast<float>(deg), tacc, bte);
+    else r = add4(bte, tacc);
+  } else if (iso.w_t != nullptr) {
+    const float* xr = iso.x + (iso.rows != nullptr ? static_cast<int64_t>(iso.rows[row]) : row) * iso.ldx;
+    float t4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < iso.c; ++c) {
+      float xv = xr[c];
+      if (iso.mean != nullptr) xv = (xv - iso.mean[c]) * iso.scale[c] + iso.beta[c];
+      if (iso.relu) xv = fmaxf(xv, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (kMain + j < p) t4[j] = fmaf(iso.w_t[static_cast<int64_t>(kMain + j) * iso.ldw + c], xv, t4[j]);
+    }
+    r = make_float4(-t4[0], -t4[1], -t4[2], -t4[3]);
+  }
+  *reinterpret_cast<float4*>(out_t + static_cast<int64_t>(row) * 4) = r;
+}
+
+template <int MODE>
+int launch_tail_mode(const FusedLayerArgs& a, cudaStream_t stream) {
+  const int n = static_cast<int>(a.n_nodes);
+  const unsigned blocks = div_up(static_cast<int64_t>(n) * 8, 256);
+#define RGNN_TAIL_CASE(DE_)                                                                                         \
+  case DE_:                                                                                                         \
+    tail_reduce_kernel<MODE, DE_><<<blocks, 256, 0, stream>>>(a.bt, a.p, a.bias_msg, a.w_e, a.ldwe, a.ea, a.csc_ptr, \
+                                                               a.csc_src, n, a.mt, a.iso);                          \
+    break;
+  switch (a.de) {
+    RGNN_TAIL_CASE(1) RGNN_TAIL_CASE(2) RGNN_TAIL_CASE(3) RGNN_TAIL_CASE(4)
+    default: return RGNN_ERR_UNSUPPORTED;
+  }
+#undef RGNN_TAIL_CASE
+  RGNN_LAUNCH_CHECK();
+  return RGNN_OK;
 }
 
 template <int MODE, int DE>
@@ -664,6 +724,14 @@ int64_t fused_layer_partials(int64_t n_nodes) {
   return div_up(n_nodes, fused_rows_per_cta(n_nodes));
 }
 
+// debug: device buffer of 1024 int64 receiving the timeline of CTA `cta` of the next launch
+static long long* g_fused_trace = nullptr;
+static int g_fused_trace_cta = 0;
+extern "C" void rgnn_debug_trace_fused_layer(void* device_buffer, int cta) {
+  g_fused_trace = static_cast<long long*>(device_buffer);
+  g_fused_trace_cta = cta;
+}
+
 int launch_fused_layer(const FusedLayerArgs& a, cudaStream_t stream) {
   if (a.n_nodes <= 0) return RGNN_OK;
   if (a.n_nodes > 0x7ffffff0LL) return RGNN_ERR_INVALID_ARGUMENT;
@@ -671,7 +739,7 @@ int launch_fused_layer(const FusedLayerArgs& a, cudaStream_t stream) {
       reinterpret_cast<uintptr_t>(a.wpack) % 16 != 0)
     return RGNN_ERR_UNSUPPORTED;
   FusedParams p{};
-  p.bm = a.bm; p.bt = a.bt; p.p = a.p; p.bias_msg = a.bias_msg; p.w_e = a.w_e; p.ldwe = a.ldwe; p.ea = a.ea;
+  p.bm = a.bm; p.mt = a.mt; p.p = a.p; p.bias_msg = a.bias_msg; p.w_e = a.w_e; p.ldwe = a.ldwe; p.ea = a.ea;
   p.csc_ptr = a.csc_ptr; p.csc_src = a.csc_src; p.iso = a.iso;
   p.x = a.x; p.ldx = a.ldx; p.x_rows = a.x_rows; p.x_mean = a.x_mean; p.x_scale = a.x_scale; p.x_beta = a.x_beta; p.relu_x = a.relu_x;
   p.wpack = a.wpack; p.w_tail = a.w_tail; p.ld_wtail = a.ld_wtail; p.bias_post = a.bias_post;
@@ -682,6 +750,18 @@ int launch_fused_layer(const FusedLayerArgs& a, cudaStream_t stream) {
   p.tiles_per_cta = (p.rows_per_cta + kRows - 1) / kRows;
   const int grid = static_cast<int>(div_up(a.n_nodes, p.rows_per_cta));
   p.n_partials = grid;
+  p.trace = g_fused_trace; p.trace_cta = g_fused_trace_cta; g_fused_trace = nullptr;
+  {
+    RGNN_PROFILE("edge_tail_reduce", stream);
+    int st = RGNN_ERR_UNSUPPORTED;
+    switch (a.aggr) {
+      case RGNN_AGGR_MAX: st = launch_tail_mode<RGNN_AGGR_MAX>(a, stream); break;
+      case RGNN_AGGR_MIN: st = launch_tail_mode<RGNN_AGGR_MIN>(a, stream); break;
+      case RGNN_AGGR_MEAN: st = launch_tail_mode<RGNN_AGGR_MEAN>(a, stream); break;
+      default: break;
+    }
+    RGNN_RETURN_IF_ERROR(st);
+  }
   RGNN_PROFILE("edge_update_fused", stream);
   switch (a.aggr) {
     case RGNN_AGGR_MAX: return launch_fused_mode<RGNN_AGGR_MAX>(p, a.de, grid, stream);
