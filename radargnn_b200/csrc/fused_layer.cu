@@ -611,10 +611,14 @@ __global__ void __launch_bounds__(256)
 tail_reduce_kernel(const float* __restrict__ bt, int p, const float* __restrict__ bias, const float* __restrict__ w_e,
                    int64_t ldwe, const float* __restrict__ ea, const int32_t* __restrict__ csc_ptr,
                    const int32_t* __restrict__ csc_src, int n_nodes, float* __restrict__ out_t, IsolatedNodeTerm iso) {
+  // 4 lanes per row, lane q takes slots q, q + 4, q + 8, q + 12 of a batch of 16: four independent
+  // index -> gather chains in flight per lane (the kernel is a chain of three dependent load rounds)
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = gid >> 3, q = threadIdx.x & 7;
+  const int row = gid >> 2, q = threadIdx.x & 3;
   const bool live = row < n_nodes;
   constexpr float kInit = MODE == RGNN_AGGR_MAX ? -INFINITY : (MODE == RGNN_AGGR_MIN ? INFINITY : 0.f);
+  int beg = 0, deg = 0;
+  if (live) { beg = csc_ptr[row]; deg = csc_ptr[row + 1] - beg; }
   float4 we[DE];
 #pragma unroll
   for (int d = 0; d < DE; ++d) {
@@ -623,18 +627,32 @@ tail_reduce_kernel(const float* __restrict__ bt, int p, const float* __restrict_
     we[d].z = kMain + 2 < p ? w_e[static_cast<int64_t>(kMain + 2) * ldwe + d] : 0.f;
     we[d].w = kMain + 3 < p ? w_e[static_cast<int64_t>(kMain + 3) * ldwe + d] : 0.f;
   }
-  int beg = 0, deg = 0;
-  if (live) { beg = csc_ptr[row]; deg = csc_ptr[row + 1] - beg; }
   float4 tacc = make_float4(kInit, kInit, kInit, kInit);
-  for (int b = q; b < deg; b += 8) {
-    const int src = csc_src[beg + b];
-    float4 t = ld4(bt + static_cast<int64_t>(src) * 4);
+  for (int b = 0; b < deg; b += 16) {
+    int src[4];
 #pragma unroll
-    for (int d = 0; d < DE; ++d) t = fma4(ea[static_cast<int64_t>(beg + b) * DE + d], we[d], t);
-    tacc = combine4<MODE>(tacc, t);
+    for (int j = 0; j < 4; ++j) src[j] = b + 4 * j + q < deg ? csc_src[beg + b + 4 * j + q] : 0;
+    float4 t[4];
+    float e[4][DE];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool on = b + 4 * j + q < deg;
+      t[j] = on ? ld4(bt + static_cast<int64_t>(src[j]) * 4) : tacc;
+#pragma unroll
+      for (int d = 0; d < DE; ++d) e[j][d] = on ? ea[static_cast<int64_t>(beg + b + 4 * j + q) * DE + d] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (b + 4 * j + q < deg) {
+        float4 tj = t[j];
+#pragma unroll
+        for (int d = 0; d < DE; ++d) tj = fma4(e[j][d], we[d], tj);
+        tacc = combine4<MODE>(tacc, tj);
+      }
+    }
   }
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) {
+  for (int o = 2; o > 0; o >>= 1) {   // fixed-order butterfly over the row's 4 lanes
     float4 other;
     other.x = __shfl_xor_sync(0xffffffffu, tacc.x, o); other.y = __shfl_xor_sync(0xffffffffu, tacc.y, o);
     other.z = __shfl_xor_sync(0xffffffffu, tacc.z, o); other.w = __shfl_xor_sync(0xffffffffu, tacc.w, o);
@@ -666,7 +684,7 @@ tail_reduce_kernel(const float* __restrict__ bt, int p, const float* __restrict_
 template <int MODE>
 int launch_tail_mode(const FusedLayerArgs& a, cudaStream_t stream) {
   const int n = static_cast<int>(a.n_nodes);
-  const unsigned blocks = div_up(static_cast<int64_t>(n) * 8, 256);
+  const unsigned blocks = div_up(static_cast<int64_t>(n) * 4, 256);
 #define RGNN_TAIL_CASE(DE_)                                                                                         \
   case DE_:                                                                                                         \
     tail_reduce_kernel<MODE, DE_><<<blocks, 256, 0, stream>>>(a.bt, a.p, a.bias_msg, a.w_e, a.ldwe, a.ea, a.csc_ptr, \

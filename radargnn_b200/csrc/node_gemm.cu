@@ -33,10 +33,12 @@ using namespace tc;   // kRows, kKc, kABufFloats and the inline-PTX helpers (tc_
 // ---- weight packing ------------------------------------------------------------------------
 // image = per 32-float K block one swizzled [np x 32] panel of hi parts directly followed by the panel of
 // lo parts, so that a single B descriptor with N = 2 np covers [W_hi ; W_lo] of the block
+// (np = padded width of one output-column chunk, rows chunks * np in total: chunk c of the image is the
+// complete K-block sequence of output rows c * np .. c * np + np - 1)
 __global__ void __launch_bounds__(256)
-pack_weights_kernel(TcWeightBlocks blocks, int np, int kp, float* __restrict__ out) {
+pack_weights_kernel(TcWeightBlocks blocks, int np, int chunks, int kp, float* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= np * kp) return;   // kp: multiple of 32 here
+  if (idx >= chunks * np * kp) return;   // kp: multiple of 32 here
   const int nrow = idx / kp, kcol = idx - nrow * kp;
   float v = 0.f;
   for (int b = 0; b < blocks.count; ++b) {
@@ -48,7 +50,8 @@ pack_weights_kernel(TcWeightBlocks blocks, int np, int kp, float* __restrict__ o
   }
   float hi, lo;
   split_tf32(v, hi, lo);
-  const int off = (kcol >> 5) * (2 * np * 32) + sw128_offset(nrow, (kcol & 31) >> 2) + (kcol & 3);
+  const int chunk = nrow / np, r = nrow - chunk * np;
+  const int off = chunk * (2 * np * kp) + (kcol >> 5) * (2 * np * 32) + sw128_offset(r, (kcol & 31) >> 2) + (kcol & 3);
   out[off] = hi;
   out[np * 32 + off] = lo;
 }
@@ -101,7 +104,7 @@ constexpr int kProducerWarps = kEpiWarp0;         // warps in front of the epilo
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kMmaWarp = kEpiWarp0 + kEpilogueThreads / 32;
 constexpr int kGemmThreads = (kMmaWarp + 1) * 32;
-constexpr int kMaxPanels = 16;
+constexpr int kMaxPanels = 32;
 constexpr int kAStageCols = 64;                   // TMEM columns of one A stage: 32 hi + 32 lo
 
 enum PanelFlags : int32_t { kPanelBn = 1, kPanelRelu = 2, kPanelRowScale = 4, kPanelGather = 8, kPanelBulk = 16, kPanelTmaA1 = 32, kPanelTmaAt = 64 };
@@ -164,6 +167,15 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   uint64_t* acc_empty = acc_full + 2;                  // [2]
 
   uint64_t* setup_bar = acc_empty + 2;
+  // Output-column chunks: a CTA works on ONE chunk of np columns (its slice of W stays resident) and on the
+  // row tiles cta_c, cta_c + ctas_c, ... -- wide outputs / long K (d = 128 layers) do not fit shared memory
+  // with all of W, the A panels are then re-streamed once per chunk (from L2)
+  const int n_chunks = p.n_chunks;
+  const int ck = static_cast<int>(blockIdx.x) % n_chunks, cta_c = static_cast<int>(blockIdx.x) / n_chunks;
+  const int ctas_c = static_cast<int>(gridDim.x) / n_chunks;
+  const int col0 = ck * np;                               // first output column of the chunk
+  const int n_loc = min(np, p.n - col0);                  // valid / stored columns of the chunk
+  const int n_store_loc = min(np, p.n_store - col0);
   const bool dual = p.dual != 0;   // one MMA per k-step for hi*hi and hi*lo: N = 2 np against [W_hi ; W_lo]
   const int acc_stride = dual ? 2 * np : np;   // TMEM columns of one accumulator
 
@@ -218,7 +230,7 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   const uint32_t a_col0 = static_cast<uint32_t>(2 * acc_stride);   // A stages follow the two accumulators
 
   const int64_t n_tiles = (p.m + kRows - 1) / kRows;
-  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t my_tiles = cta_c < n_tiles ? (n_tiles - cta_c + ctas_c - 1) / ctas_c : 0;
   const int total = static_cast<int>(my_tiles) * panels;   // panels this CTA streams
   const int m32 = static_cast<int>(p.m);
   bool timed_out = false;
@@ -237,7 +249,7 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     uint32_t wrap = 0;   // how often the ring has wrapped
     int32_t rr[kLoaderItems];   // source rows of this thread's items (through the optional gather map), per tile; -1: none
     auto tile_rows = [&](int t) {
-      const int row0 = static_cast<int>(blockIdx.x + static_cast<int64_t>(t) * gridDim.x) * kRows;
+      const int row0 = static_cast<int>(cta_c + static_cast<int64_t>(t) * ctas_c) * kRows;
 #pragma unroll
       for (int i = 0; i < kLoaderItems; ++i) {
         const int row = row0 + rsub + 4 * i;
@@ -250,7 +262,7 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     // load needs more, so the tiles two ahead are pulled into L2 and the ring's copies become L2 hits
     auto l2_prefetch_tile = [&](int t) {
       if (t >= my_tiles) return;
-      const int64_t tile = blockIdx.x + static_cast<int64_t>(t) * gridDim.x;
+      const int64_t tile = cta_c + static_cast<int64_t>(t) * ctas_c;
       const int64_t row0 = tile * kRows;
       const uint32_t rows = static_cast<uint32_t>(p.m - row0 < kRows ? p.m - row0 : kRows);
       if (p.a1_rows == nullptr && (p.lda1 & 3) == 0) {
@@ -277,7 +289,7 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       if (trace != nullptr && tid == 0 && pi == 0 && tl < 32) trace[0 * 64 + tl * 2] = clock64();
       if (wrap >= 1u && !mbar_wait(&raw_empty[slot], (wrap - 1u) & 1u)) timed_out = true;
       const PanelInfo& info = s.panel[pi];
-      const int row0 = static_cast<int>(blockIdx.x + static_cast<int64_t>(tl) * gridDim.x) * kRows;
+      const int row0 = static_cast<int>(cta_c + static_cast<int64_t>(tl) * ctas_c) * kRows;
       const bool col_ok = 4 * c < info.valid;
       const float* colp = info.base + info.col0 + 4 * c;
       const bool gather = (info.flags & kPanelGather) != 0;
@@ -287,7 +299,7 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         // panel-major operand: the whole panel is one contiguous 16 KB block, already in the ring's
         // swizzled layout -> a single bulk copy that completes on the barrier's transaction count
         if (tid == 0) {
-          const int64_t tile = blockIdx.x + static_cast<int64_t>(tl) * gridDim.x;
+          const int64_t tile = cta_c + static_cast<int64_t>(tl) * ctas_c;
           const float* src = info.base + ((tile * ld + (info.col0 >> 5)) << 12);
           const uint32_t bar = smem_u32(&raw_full[slot]);
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kABufFloats * 4u) : "memory");
@@ -359,7 +371,7 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       if (flags != 0) {
         // transform in place: BatchNorm + ReLU of the previous layer on load, row scale.  Rows and columns
         // beyond the operand were zero-filled by the loaders and must stay zero after the affine map.
-        const int row = static_cast<int>(blockIdx.x + static_cast<int64_t>(tl) * gridDim.x) * kRows + rl;
+        const int row = static_cast<int>(cta_c + static_cast<int64_t>(tl) * ctas_c) * kRows + rl;
         const bool row_ok = row < m32;
         float rs = 1.f;
         if ((flags & kPanelRowScale) && row_ok) {
@@ -471,9 +483,10 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
       const int et0 = tid - kProducerThreads;
       const int total16 = (2 * np * kp32) >> 2;
       const uint32_t w_addr = smem_u32(s.w);
-      for (int i = et0; i < total16; i += kEpilogueThreads) cp_async16(w_addr + i * 16u, p.wpack + i * 4, 16);
+      const float* wsrc = p.wpack + static_cast<size_t>(ck) * (2 * static_cast<size_t>(np) * kp32);
+      for (int i = et0; i < total16; i += kEpilogueThreads) cp_async16(w_addr + i * 16u, wsrc + i * 4, 16);
       asm volatile("cp.async.commit_group;" ::: "memory");
-      for (int i = et0; i < np; i += kEpilogueThreads) s.bias[i] = (p.bias != nullptr && i < p.n) ? p.bias[i] : 0.f;
+      for (int i = et0; i < np; i += kEpilogueThreads) s.bias[i] = (p.bias != nullptr && i < n_loc) ? p.bias[col0 + i] : 0.f;
       if (p.a1_mean != nullptr) {
         const int k1r = (p.k1 + 3) & ~3;
         for (int i = et0; i < p.k1; i += kEpilogueThreads) {
@@ -494,7 +507,7 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     const int et = tid - kProducerThreads;     // 0..255
     for (int64_t tl = 0; tl < my_tiles; ++tl) {
       const int ab = static_cast<int>(tl & 1);
-      const int64_t tile = blockIdx.x + tl * gridDim.x;
+      const int64_t tile = cta_c + tl * ctas_c;
       const int64_t row = tile * kRows + q * 32 + lane;
       const bool row_ok = row < p.m;
       float* yrow = p.y + (row_ok ? row : 0) * p.ldy;
@@ -553,21 +566,21 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
           if (etr) trace[3 * 64 + 3 + (cd >> 1) * 4] = clock64();
           const int col = cd * 32 + c4 * 4;
           float4 csum4 = make_float4(0.f, 0.f, 0.f, 0.f), csq4 = csum4;
-          if (col < p.n_store && col < np) {
+          if (col < n_store_loc && col < np) {
             const float4 bv = *reinterpret_cast<const float4*>(s.bias + col);
             // split output: columns from n_split on go to the narrow tail array y2
             float* dst;
             int64_t ld;
-            if (col < n_split) { ld = p.ldy; dst = p.y + (tile_row0 + rsub) * ld + col; }
+            if (col < n_split) { ld = p.ldy; dst = p.y + (tile_row0 + rsub) * ld + col0 + col; }
             else { ld = p.ldy2; dst = p.y2 + (tile_row0 + rsub) * ld + (col - n_split); }
             const float* srow = st + rsub * 36 + c4 * 4;
             // residual (RadarPointGNNConv): the layer input, normalised on load like the A operand
-            const bool has_res = p.residual != nullptr && col < p.n;
+            const bool has_res = p.residual != nullptr && col < n_loc;
             float4 rmu = make_float4(0.f, 0.f, 0.f, 0.f), rsc = make_float4(1.f, 1.f, 1.f, 1.f), rbe = rmu;
             if (has_res && p.res_mean != nullptr) {
-              rmu = *reinterpret_cast<const float4*>(p.res_mean + col);
-              rsc = *reinterpret_cast<const float4*>(p.res_scale + col);
-              rbe = *reinterpret_cast<const float4*>(p.res_beta + col);
+              rmu = *reinterpret_cast<const float4*>(p.res_mean + col0 + col);
+              rsc = *reinterpret_cast<const float4*>(p.res_scale + col0 + col);
+              rbe = *reinterpret_cast<const float4*>(p.res_beta + col0 + col);
             }
             if (!has_res && p.bn_partial == nullptr) {
 #pragma unroll
@@ -587,7 +600,7 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
                 if (has_res) {
                   const int64_t grow = tile_row0 + rsub + it * 4;
                   const int64_t rrow_i = p.a1_rows != nullptr ? static_cast<int64_t>(p.a1_rows[grow]) : grow;
-                  float4 rv = *reinterpret_cast<const float4*>(p.residual + rrow_i * p.ldr + col);
+                  float4 rv = *reinterpret_cast<const float4*>(p.residual + rrow_i * p.ldr + col0 + col);
                   if (p.res_mean != nullptr) {
                     rv.x = (rv.x - rmu.x) * rsc.x + rbe.x; rv.y = (rv.y - rmu.y) * rsc.y + rbe.y;
                     rv.z = (rv.z - rmu.z) * rsc.z + rbe.z; rv.w = (rv.w - rmu.w) * rsc.w + rbe.w;
@@ -631,7 +644,7 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
           for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
         }
         float v[16];
-        const bool full_block = cb * 16 + 16 <= p.n;   // no padding columns inside this block
+        const bool full_block = cb * 16 + 16 <= n_loc;   // no padding columns inside this block
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 bv = *reinterpret_cast<const float4*>(s.bias + cb * 16 + j4 * 4);  // zero beyond n
@@ -643,15 +656,15 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         if (!full_block) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (cb * 16 + j >= p.n) v[j] = 0.f;
+            if (cb * 16 + j >= n_loc) v[j] = 0.f;
         }
         if (rrow != nullptr && row_ok) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = cb * 16 + j;
-            if (col < p.n) {
-              float rv = rrow[col];
-              if (p.res_mean != nullptr) rv = (rv - p.res_mean[col]) * p.res_scale[col] + p.res_beta[col];
+            if (col < n_loc) {
+              float rv = rrow[col0 + col];
+              if (p.res_mean != nullptr) rv = (rv - p.res_mean[col0 + col]) * p.res_scale[col0 + col] + p.res_beta[col0 + col];
               if (p.res_relu) rv = fmaxf(rv, 0.f);
               v[j] += rv;
             }
@@ -662,14 +675,14 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const int col = cb * 16 + j4 * 4;
-              if (full_block || col < p.n_store)
-                *reinterpret_cast<float4*>(yrow + col) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+              if (full_block || col < n_store_loc)
+                *reinterpret_cast<float4*>(yrow + col0 + col) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int col = cb * 16 + j;
-              if (col < p.n_store) yrow[col] = v[j];
+              if (col < n_store_loc) yrow[col0 + col] = v[j];
             }
           }
         }
@@ -706,15 +719,15 @@ node_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the four quarters' column sums are in shared memory
         const float* cs = s.col_sum + ab * 4 * np;
         const float* cq = s.col_sq + ab * 4 * np;
-        for (int c = et; c < p.n; c += kEpilogueThreads) {
+        for (int c = et; c < n_loc; c += kEpilogueThreads) {
           const double sum = (static_cast<double>(cs[c]) + static_cast<double>(cs[np + c])) +
                              (static_cast<double>(cs[2 * np + c]) + static_cast<double>(cs[3 * np + c]));
           const double sq2 = (static_cast<double>(cq[c]) + static_cast<double>(cq[np + c])) +
                              (static_cast<double>(cq[2 * np + c]) + static_cast<double>(cq[3 * np + c]));
           // channel-major: partial[ch * T + tile] (sums), partial[(n + ch) * T + tile] (squares), so that the
           // finalisation reads every channel's partials contiguously
-          p.bn_partial[static_cast<int64_t>(c) * n_tiles + tile] = sum;
-          p.bn_partial[static_cast<int64_t>(p.n + c) * n_tiles + tile] = sq2;
+          p.bn_partial[static_cast<int64_t>(col0 + c) * n_tiles + tile] = sum;
+          p.bn_partial[static_cast<int64_t>(p.n + col0 + c) * n_tiles + tile] = sq2;
         }
       }
     }
@@ -766,6 +779,24 @@ int pick_raw_slots(int np, int kp, int staged) {
 
 }  // namespace
 
+// Output-column chunking: the fewest chunks whose slice of W (hi + lo images, np x kp each) fits shared memory
+// next to the coalesced epilogue's transpose buffers and a raw ring of at least three panels; failing that,
+// the fewest chunks that fit at all.  {0, 0}: the contraction does not fit this kernel.
+TcChunking tc_chunking(const TcGemmShape& sh) {
+  TcChunking c{0, 0};
+  if (sh.n < 1) return c;
+  const int kp = tc_padded_k(sh);
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int nc = 1; nc <= 16; ++nc) {
+      const int np = tc_padded_n((sh.n + nc - 1) / nc);
+      if (np > 256) continue;
+      const bool ok = pass == 0 ? pick_raw_slots(np, kp, 1) >= 3 : pick_raw_slots(np, kp, 0) >= 2;
+      if (ok) { c.n_chunks = (sh.n + np - 1) / np; c.np = np; return c; }
+    }
+  }
+  return c;
+}
+
 bool tc_gemm_supported(const TcGemmShape& sh) {
   static int enabled = -1;
   if (enabled < 0) {
@@ -775,13 +806,12 @@ bool tc_gemm_supported(const TcGemmShape& sh) {
   if (!enabled) return false;
   if (sh.k1 < 4 || sh.k1 % 4 != 0 || sh.k2 % 4 != 0 || sh.n < 1) return false;
   if (sh.kt % 4 != 0) return false;
-  const int np = tc_padded_n(sh.n), kp = tc_padded_k(sh);
-  if (np > 256) return false;
-  return pick_raw_slots(np, kp, 0) > 0;
+  return tc_chunking(sh).n_chunks > 0;
 }
 
 size_t tc_pack_floats(const TcGemmShape& sh) {
-  return 2 * static_cast<size_t>(tc_padded_n(sh.n)) * tc_padded_k(sh);
+  const TcChunking c = tc_chunking(sh);
+  return 2 * static_cast<size_t>(c.n_chunks) * c.np * tc_padded_k(sh);
 }
 
 int tc_fold_weights(const float* w_m, int64_t ld_m, const float* w_t, int64_t ld_t, int c_out, int p, int c,
@@ -793,9 +823,11 @@ int tc_fold_weights(const float* w_m, int64_t ld_m, const float* w_t, int64_t ld
 }
 
 int tc_pack_weights(const TcWeightBlocks& blocks, const TcGemmShape& sh, float* wpack, cudaStream_t stream) {
-  const int np = tc_padded_n(sh.n), kp = tc_padded_k(sh);
+  const TcChunking c = tc_chunking(sh);
+  if (c.n_chunks < 1) return RGNN_ERR_UNSUPPORTED;
+  const int kp = tc_padded_k(sh);
   RGNN_PROFILE("weight_prep", stream);
-  pack_weights_kernel<<<div_up(np * kp, 256), 256, 0, stream>>>(blocks, np, kp, wpack);
+  pack_weights_kernel<<<div_up(static_cast<int64_t>(c.n_chunks) * c.np * kp, 256), 256, 0, stream>>>(blocks, c.np, c.n_chunks, kp, wpack);
   RGNN_LAUNCH_CHECK();
   return RGNN_OK;
 }
@@ -848,8 +880,14 @@ static bool encode_panel_map(CUtensorMap* tm, const float* base, int64_t rows, i
 int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
   if (p.m <= 0) return RGNN_OK;
   if (g_trace_buffer != nullptr && strcmp(tag, g_trace_tag) == 0 && g_trace_skip-- <= 0) { p.trace = g_trace_buffer; g_trace_buffer = nullptr; }
-  p.np = tc_padded_n(p.n);
   p.kp = tc_seg_pad(p.k1) + tc_seg_pad(p.k2) + tc_seg_pad(p.kt) + tc_seg_pad(p.k3);
+  {
+    TcGemmShape sh; sh.k1 = p.k1; sh.k2 = p.k2; sh.kt = p.kt; sh.k3 = p.k3; sh.n = p.n;
+    const TcChunking c = tc_chunking(sh);
+    if (c.n_chunks < 1) return RGNN_ERR_UNSUPPORTED;
+    p.np = c.np; p.n_chunks = c.n_chunks;
+  }
+  if (p.n_chunks > 1 && p.y2 != nullptr) return RGNN_ERR_UNSUPPORTED;   // split outputs are single-chunk shapes
   if (p.n_store < p.n) p.n_store = p.n;
   p.a_stages = pick_a_stages(p.np);
   p.dual = pick_dual(p.np) ? 1 : 0;
@@ -889,7 +927,11 @@ int launch_tc_gemm(TcGemmParams p, const char* tag, cudaStream_t stream) {
   static bool configured[kMaxDevices] = {};
   RGNN_CUDA_CHECK(opt_in_dynamic_smem(node_gemm_kernel, configured, 227 * 1024));
   const int64_t tiles = (p.m + kRows - 1) / kRows;
-  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  // CTA b works on chunk b % n_chunks: a multiple of n_chunks CTAs, at most one per SM
+  int per_chunk = sm_count() / p.n_chunks;
+  if (per_chunk < 1) per_chunk = 1;
+  if (tiles < per_chunk) per_chunk = static_cast<int>(tiles);
+  const int grid = per_chunk * p.n_chunks;
   RGNN_PROFILE(tag, stream);
   node_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(p);
   RGNN_LAUNCH_CHECK();

@@ -44,7 +44,7 @@ struct TcGemmParams {
   const float* a1_mean = nullptr; const float* a1_scale = nullptr; const float* a1_beta = nullptr;
   int32_t relu_a1 = 0, relu_a2 = 0;
   const float* wpack = nullptr;                                  // tc_pack_weights image
-  int32_t n = 0, np = 0, kp = 0, a_stages = 0, raw_slots = 0, staged_epilogue = 0, dual = 0, conv_groups = 0;
+  int32_t n = 0, np = 0, n_chunks = 1, kp = 0, a_stages = 0, raw_slots = 0, staged_epilogue = 0, dual = 0, conv_groups = 0;
   const float* bias = nullptr;
   const float* residual = nullptr; int64_t ldr = 0;
   const float* res_mean = nullptr; const float* res_scale = nullptr; const float* res_beta = nullptr;
@@ -69,6 +69,9 @@ __host__ __device__ inline int64_t tc_panel_offset(int64_t row, int col, int pan
 }
 inline size_t tc_panel_major_floats(int64_t rows, int k) { return static_cast<size_t>((rows + 127) / 128) * 128 * k; }
 
+// how the N output columns are split into chunks of np (padded) columns, one chunk per CTA (node_gemm.cu)
+struct TcChunking { int32_t n_chunks, np; };
+TcChunking tc_chunking(const TcGemmShape& sh);
 bool tc_gemm_supported(const TcGemmShape& sh);
 size_t tc_pack_floats(const TcGemmShape& sh);
 int64_t tc_tiles(int64_t m);
