@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RGNN_ABI_VERSION 2
+#define RGNN_ABI_VERSION 3
 
 typedef void* rgnn_stream_t; /* cudaStream_t */
 
@@ -257,6 +257,58 @@ int rgnn_sum_f32(const float* x, int64_t count, double* result, void* workspace,
 int rgnn_linear_forward(const float* x, int64_t n, int32_t in_features, const float* weight,
                         const float* bias, int32_t out_features, int32_t relu_input, float* y,
                         rgnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* callers either side of the path                               */
+/* ------------------------------------------------------------------------------------ */
+/* Loss of the detection heads (gnn/trainer.py:184-206 training, 276-298 validation):
+ *   loss_cls = torch.nn.CrossEntropyLoss(weight = class_weight)(cls, y[:, 0].long())  (weighted mean; label -100 ignored)
+ *   loss_bb  = mean over the nodes with y[:, 0] != bg_index of torch.nn.HuberLoss(delta)(y[i, 1:], bb[i])
+ *              (0 without such a node; nan_to_zero: a NaN box loss counts as 0, trainer.py:206-216)
+ *   loss     = cls_loss_weight * loss_cls + bb_loss_weight * loss_bb
+ * cls [N, n_classes], bb [N, n_box], y [N, ldy >= 1 + n_box] (label stored as float, like graph_batch.y).
+ * out (DEVICE double[5]) = loss, loss_cls, loss_bb, number of foreground nodes, number of labels outside
+ * [0, n_classes) (torch raises an index error for those; they are left out of the sums).  Replaces the
+ * reference's per-node Python loop by one deterministic reduction (fp64, fixed order). */
+size_t rgnn_detection_loss_workspace_bytes(void);
+int rgnn_detection_loss(const float* cls, int32_t n_classes, const float* bb, int32_t n_box, const float* y, int64_t ldy,
+                        int64_t n_nodes, const float* class_weight, int32_t bg_index, float cls_loss_weight,
+                        float bb_loss_weight, float huber_delta, int32_t nan_to_zero, double* out, void* workspace,
+                        size_t workspace_bytes, rgnn_stream_t stream);
+
+/* Greedy non-maximum suppression (postprocessor/postprocessing.py:336-435).
+ *   rotated == 0: boxes f32 [n, 4] (x1, y1, x2, y2), scores f32 [n]: torchvision.ops.nms (:408);
+ *   rotated == 1: boxes f64 [n, 5] (cx, cy, w, h, angle in degrees), scores f64 [n]: detectron2 nms_rotated (:370).
+ * A box is dropped when its IoU with a kept box of higher score (ties: lower index first) exceeds
+ * iou_threshold.  shift_negative reproduces the reference moving all boxes by |min| + 100 when a coordinate
+ * is negative (:361-365, :400-404).  box_frame (int32 [n], may be NULL): boxes of different frames never
+ * suppress each other.  keep (int64 [n]) receives the kept indices ordered by (frame, descending score),
+ * *keep_count (device int32) their number, keep_flag (uint8 [n]) one flag per box.  n <= 65536. */
+size_t rgnn_nms_workspace_bytes(int64_t n_boxes);
+int rgnn_nms(const void* boxes, int32_t rotated, const void* scores, const int32_t* box_frame, int64_t n_boxes,
+             double iou_threshold, int32_t shift_negative, int64_t* keep, int32_t* keep_count, uint8_t* keep_flag,
+             void* workspace, size_t workspace_bytes, rgnn_stream_t stream);
+
+/* Nearest neighbour of every point inside its frame -- kneighbors_graph(X, 1, include_self=False) followed by
+ * X[np.where(A == 1)[1]] (preprocessor/radarscenes/dataset_creation.py:314-318, nuscenes/conversion.py:133-137,
+ * postprocessor/postprocessing.py:233-237, 468-472).  nn_index int64 [N] (-1 for the point of a one-point
+ * frame), nn_points [N, dims] of the basis dtype (row untouched where there is no neighbour); either may be NULL. */
+size_t rgnn_nearest_neighbor_workspace_bytes(int64_t n_points, int32_t n_frames);
+int rgnn_nearest_neighbor(const void* basis, int32_t basis_dtype, int32_t dims, const int64_t* frame_ptr_host, int32_t n_frames,
+                          int64_t* nn_index, void* nn_points, void* workspace, size_t workspace_bytes, rgnn_stream_t stream);
+
+/* time_index node feature (dataset_creation.py:214-223): position of the point's timestamp among the sorted
+ * distinct timestamps of its frame, as double.  frame_ptr (device) and frame_ptr_host hold the same
+ * [n_frames + 1] offsets; a frame may hold at most 8192 points. */
+int rgnn_time_index(const double* timestamp, const int64_t* frame_ptr, const int64_t* frame_ptr_host, int32_t n_frames,
+                    double* time_index, rgnn_stream_t stream);
+
+/* Node-id offsets of the disjoint-union collate (utils/data_handling.py:30, PyG Batch.from_data_list):
+ * edge_index [2, E] holds frame-local ids, columns edge_ptr[f] .. edge_ptr[f+1] belong to frame f (device
+ * int64 [n_frames + 1] tables); both rows get node_ptr[f] added in place.  batch_of_node (int64 [n_nodes], may be
+ * NULL) receives PyG's `batch` vector. */
+int rgnn_collate_offsets(int64_t* edge_index, int64_t n_edges, const int64_t* edge_ptr, const int64_t* node_ptr, int32_t n_frames,
+                         int64_t n_nodes, int64_t* batch_of_node, rgnn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------ */
 /* fused path: graph build + L-layer MPNN forward (the north-star hot path)               */

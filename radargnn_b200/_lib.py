@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "librgnn_b200.so")
 OK, ERR_INVALID_ARGUMENT, ERR_K_NOT_SMALLER_THAN_N, ERR_WORKSPACE_TOO_SMALL, ERR_CUDA, \
     ERR_DOT_PRODUCT, ERR_INVALID_FEATURE, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_NON_FINITE_INPUT, \
     ERR_INDEX_OUT_OF_RANGE = range(11)
-ABI_VERSION = 2
+ABI_VERSION = 3
 F32, F64 = 0, 1
 DIRECTED, UNDIRECTED = 0, 1
 EDGE_FEATURES = {
@@ -117,6 +117,19 @@ _PROTOTYPES = {
     "rgnn_sum_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rgnn_linear_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_void_p, C.c_void_p]),
+    "rgnn_detection_loss_workspace_bytes": (C.c_size_t, []),
+    "rgnn_detection_loss": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
+                                      C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p,
+                                      C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rgnn_nms_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "rgnn_nms": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int32, C.c_void_p,
+                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rgnn_nearest_neighbor_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "rgnn_nearest_neighbor": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rgnn_time_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "rgnn_collate_offsets": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
+                                       C.c_void_p]),
     "rgnn_pipeline_workspace_bytes": (C.c_size_t, [C.POINTER(PipelineDesc), C.c_int64, C.c_int32, C.c_int64]),
     "rgnn_pipeline_forward": (C.c_int, [C.POINTER(PipelineDesc), C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,

@@ -509,3 +509,114 @@ def pipeline_forward_host(cfg: PipelineConfig, pos: np.ndarray, vel: np.ndarray,
             None if edge_attr is None else edge_attr.ctypes.data, h.ctypes.data, ws.data_ptr(), ws.numel(),
             _lib.stream_ptr()))
     return edge_index, edge_attr, h
+
+
+# ---------------------------------------------------------------------------------------------
+# callers either side of the path: loss, NMS, nearest neighbour, time index, collate
+# ---------------------------------------------------------------------------------------------
+def detection_loss(cls: torch.Tensor, bb: torch.Tensor, y: torch.Tensor, class_weight: Optional[torch.Tensor],
+                   bg_index: int, cls_loss_weight: float = 1.0, bb_loss_weight: float = 1.0, huber_delta: float = 1.0,
+                   nan_to_zero: bool = True) -> torch.Tensor:
+    """Weighted cross entropy + Huber box loss over the foreground nodes (reference gnn/trainer.py:184-231).
+    Returns a DEVICE double[5]: loss, loss_cls, loss_bb, foreground nodes, labels outside [0, n_classes)."""
+    _lib.require_device()
+    lib = _lib.load()
+    cls = _cuda_contig(cls.to(torch.float32), "cls")
+    bb = _cuda_contig(bb.to(torch.float32), "bb")
+    y = _cuda_contig(y.to(torch.float32), "y")
+    n, k = cls.shape
+    nb = bb.shape[1] if bb.dim() == 2 else 0
+    if y.shape[0] != n or bb.shape[0] != n or y.shape[1] < 1 + nb:
+        raise ValueError("cls [N, K], bb [N, B] and y [N, 1 + B] must agree")
+    w = None if class_weight is None else _cuda_contig(class_weight.to(torch.float32), "class_weight")
+    if w is not None and w.numel() != k:
+        raise ValueError("class_weight needs one entry per class")
+    out = torch.empty(5, dtype=torch.float64, device=cls.device)
+    with torch.cuda.device(cls.device):
+        ws = _lib.workspace(lib.rgnn_detection_loss_workspace_bytes(), cls.device)
+        _lib.check(lib.rgnn_detection_loss(cls.data_ptr(), k, bb.data_ptr(), nb, y.data_ptr(), y.shape[1], n, _lib.ptr(w),
+                                           int(bg_index), float(cls_loss_weight), float(bb_loss_weight), float(huber_delta),
+                                           1 if nan_to_zero else 0, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           _lib.stream_ptr()))
+    return out
+
+
+def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float, rotated: bool = False,
+        box_frame: Optional[torch.Tensor] = None, shift_negative: bool = True) -> torch.Tensor:
+    """Greedy NMS (postprocessor/postprocessing.py:336-435): kept indices (int64) by (frame, descending score).
+    aligned: boxes [n, 4] (x1, y1, x2, y2) fp32 (torchvision.ops.nms); rotated: [n, 5] (cx, cy, w, h, degrees) fp64."""
+    _lib.require_device()
+    lib = _lib.load()
+    dt = torch.float64 if rotated else torch.float32
+    boxes = _cuda_contig(boxes.to(dt), "boxes")
+    scores = _cuda_contig(scores.to(dt).reshape(-1), "scores")
+    n = boxes.shape[0]
+    if boxes.dim() != 2 or boxes.shape[1] != (5 if rotated else 4) or scores.numel() != n:
+        raise ValueError("boxes must be [n, 4] (aligned) or [n, 5] (rotated) with one score per box")
+    fr = None if box_frame is None else _cuda_contig(box_frame.to(torch.int32), "box_frame")
+    keep = torch.empty(n, dtype=torch.int64, device=boxes.device)
+    count = torch.zeros(1, dtype=torch.int32, device=boxes.device)
+    flag = torch.empty(n, dtype=torch.uint8, device=boxes.device)
+    with torch.cuda.device(boxes.device):
+        nbytes = lib.rgnn_nms_workspace_bytes(n)
+        if n > 0 and nbytes == 0:
+            raise ValueError("nms handles at most 65536 boxes per call")
+        ws = _lib.workspace(nbytes, boxes.device)
+        _lib.check(lib.rgnn_nms(boxes.data_ptr(), 1 if rotated else 0, scores.data_ptr(), _lib.ptr(fr), n, float(iou_threshold),
+                                1 if shift_negative else 0, keep.data_ptr(), count.data_ptr(), flag.data_ptr(),
+                                ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    return keep[: int(count.item())]
+
+
+def nearest_neighbor(basis: torch.Tensor, frame_ptr=None):
+    """(nn_index int64 [N], nn_points [N, D]): kneighbors_graph(X, 1) + X[np.where(A == 1)[1]]
+    (dataset_creation.py:314-318, postprocessing.py:233-237)."""
+    _lib.require_device()
+    lib = _lib.load()
+    basis = _cuda_contig(basis, "basis")
+    if basis.dtype not in (torch.float32, torch.float64):
+        basis = basis.to(torch.float64)
+    n, d = basis.shape
+    fp = _frame_ptr(frame_ptr, n)
+    idx = torch.empty(n, dtype=torch.int64, device=basis.device)
+    pts = torch.full_like(basis, float("nan"))
+    with torch.cuda.device(basis.device):
+        ws = _lib.workspace(lib.rgnn_nearest_neighbor_workspace_bytes(n, len(fp) - 1), basis.device)
+        _lib.check(lib.rgnn_nearest_neighbor(basis.data_ptr(), _dtype_code(basis), d, fp.ctypes.data, len(fp) - 1,
+                                             idx.data_ptr(), pts.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    return idx, pts
+
+
+def time_index(timestamp: torch.Tensor, frame_ptr=None) -> torch.Tensor:
+    """Dense rank of every point's timestamp inside its frame (dataset_creation.py:214-223), float64."""
+    _lib.require_device()
+    lib = _lib.load()
+    ts = _cuda_contig(timestamp.to(torch.float64).reshape(-1), "timestamp")
+    n = ts.numel()
+    fp = _frame_ptr(frame_ptr, n)
+    fp_dev = torch.from_numpy(fp).to(ts.device)
+    out = torch.zeros(n, dtype=torch.float64, device=ts.device)
+    with torch.cuda.device(ts.device):
+        _lib.check(lib.rgnn_time_index(ts.data_ptr(), fp_dev.data_ptr(), fp.ctypes.data, len(fp) - 1, out.data_ptr(),
+                                       _lib.stream_ptr()))
+    return out
+
+
+def collate_offsets(edge_index: torch.Tensor, edge_ptr, node_ptr):
+    """PyG's disjoint-union collate of edge_index (utils/data_handling.py:30) on the device: edge_index [2, E] with
+    frame-local ids (frames concatenated) gets each frame's node offset added IN PLACE; returns (edge_index, batch)."""
+    _lib.require_device()
+    lib = _lib.load()
+    if edge_index.dtype != torch.int64 or not edge_index.is_contiguous() or not edge_index.is_cuda:
+        raise ValueError("edge_index must be a contiguous CUDA int64 [2, E] tensor")
+    ep = np.ascontiguousarray(np.asarray(edge_ptr, dtype=np.int64))
+    npt = np.ascontiguousarray(np.asarray(node_ptr, dtype=np.int64))
+    if ep.shape != npt.shape or ep[0] != 0 or npt[0] != 0 or ep[-1] != edge_index.shape[1]:
+        raise ValueError("edge_ptr / node_ptr must be [F + 1] offset tables matching edge_index")
+    dev = edge_index.device
+    ep_d, np_d = torch.from_numpy(ep).to(dev), torch.from_numpy(npt).to(dev)
+    batch = torch.empty(int(npt[-1]), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.rgnn_collate_offsets(edge_index.data_ptr(), edge_index.shape[1], ep_d.data_ptr(), np_d.data_ptr(),
+                                            len(ep) - 1, int(npt[-1]), batch.data_ptr(), _lib.stream_ptr()))
+    return edge_index, batch
