@@ -140,8 +140,9 @@ class DetNetBasic(torch.nn.Module):
     # ---- fused hot path: point cloud in, node embeddings out -----------------------------------
     def pipeline_config(self, graph_config) -> ops.PipelineConfig:
         """The conv stack + a GraphConstructionConfiguration as one fused-kernel configuration."""
-        if self.initial_node_feature_embedding or self.initial_edge_feature_embedding:
-            raise NotImplementedError("the fused path starts at the conv stack: run the embedding MLPs first")
+        if self.initial_edge_feature_embedding:
+            raise NotImplementedError("the one-call fused path feeds the conv stack with the raw edge attributes; with an "
+                                      "edge embedding MLP forward_from_points runs the stage-by-stage CUDA path instead")
         layers = [conv.conv_params() for conv in self.convs]
         bn = [(b.module.weight, b.module.bias) for b in self.batch_norms]
         # The fused kernels normalise with BATCH statistics (the reference never leaves training mode,
@@ -173,6 +174,25 @@ class DetNetBasic(torch.nn.Module):
             if not (torch.equal(pos.float().double(), pos.double()) and torch.equal(vel.float().double(), vel.double())):
                 raise ValueError("forward_from_points takes float32 coordinates; these float64 values are not "
                                  "float32-representable, so neighbours / edge_attr could differ from GraphConstructor's")
+        if self.initial_node_feature_embedding:
+            x = _run_mlp(self.node_emb_mlp, x)   # per node, independent of the graph: ahead of the fused call
+        if self.initial_edge_feature_embedding:
+            # the edge embedding MLP (gnn_models.py:120-121) sits between edge_attr and the conv stack: neighbour
+            # search, edge features, embedding and conv stack as separate CUDA stages (same kernels, one call each)
+            basis = pos if graph_config.distance_definition == "X" else torch.cat([pos, vel], dim=1)
+            if graph_config.graph_construction_algorithm == "knn":
+                edge_index = ops.knn_graph(basis, graph_config.k, frame_ptr)
+            else:
+                edge_index = ops.radius_graph(basis, graph_config.r, frame_ptr)
+            edge_attr = ops.edge_features(pos, vel, edge_index, list(graph_config.edge_features), graph_config.edge_mode,
+                                          out_dtype=torch.float32)
+            ea = _run_mlp(self.edge_emb_mlp, edge_attr)
+            h = x
+            for conv, batch_norm in zip(self.convs, self.batch_norms):
+                h = batch_norm(conv(h, edge_index, ea), relu=True)
+            if not heads:
+                return edge_index, edge_attr, h
+            return edge_index, edge_attr, _run_mlp(self.classification_head, h), _run_mlp(self.regression_head, h)
         edge_index, edge_attr, h = ops.pipeline_forward(self.pipeline_config(graph_config), pos, vel, x, frame_ptr)
         for b in self.batch_norms:   # torch.nn.BatchNorm1d bookkeeping of a training-mode forward
             if b.module.num_batches_tracked is not None:

@@ -268,6 +268,42 @@ def test_detnet_fused_path_equals_layerwise(gnn):
         model.forward_from_points(gcfg, pos.double() + 1e-9, vel.double(), x, ptr)
 
 
+def test_detnet_with_embedding_mlps_from_points(gnn):
+    """The shipped architecture shape (configurations/configuration_radarscenes.yml:18-42: node and edge embedding
+    MLPs in front of the conv stack) from a point cloud: forward_from_points == graph ops + forward()."""
+    from radargnn_b200 import ops, synthetic
+    from radargnn_b200.preprocessor import GraphConstructionConfiguration
+    torch.manual_seed(1)
+    cfg = gnn.GNNArchitectureConfig(5, 4, [32, 32, 16], [8, 4], [8, 5], initial_node_feature_embedding=True,
+                                    initial_edge_feature_embedding=True, node_feature_embedding_layer_dimensions=[8, 16],
+                                    edge_feature_embedding_layer_dimensions=[4, 8, 16], batch_norm_in_mlps=False)
+    model = gnn.DetNetBasic(cfg).to(DEV)
+    gcfg = GraphConstructionConfiguration("knn", {"k": 6}, ["rcs"], ["point_pair_features"], "directed", "X")
+    frames = [synthetic.radar_frame(150, seed=s) for s in range(2)]
+    X, V, ptr = synthetic.frame_batch(frames)
+    pos, vel = torch.tensor(X, dtype=torch.float32, device=DEV), torch.tensor(V, dtype=torch.float32, device=DEV)
+    x = torch.randn(X.shape[0], 5, device=DEV)
+    ei, ea, c, bb = model.forward_from_points(gcfg, pos, vel, x, ptr)
+    np.testing.assert_array_equal(ei.cpu().numpy().T, go.batched_edges([f.X_cc for f in frames], "knn", k=6))
+    assert ea.shape == (ei.shape[1], 4) and c.shape == (X.shape[0], 4) and bb.shape == (X.shape[0], 5)
+    c2, bb2 = model(x, ei, ea)
+    assert mo.relative_error(c, c2) <= 1e-5 and mo.relative_error(bb, bb2) <= 1e-5
+    # ... and against plain torch modules holding the same parameters (fp64)
+    want_c, want_bb = mo.det_net_forward({k: v.detach().cpu() for k, v in model.state_dict().items()}, x.cpu(), ei.cpu(), ea.cpu(),
+                                         n_layers=3, node_embedding=True, edge_embedding=True, dtype=torch.float64)
+    assert mo.relative_error(c.cpu(), want_c) <= 1e-4 and mo.relative_error(bb.cpu(), want_bb) <= 1e-4
+    # node embedding only: the one-call fused path takes the embedded x
+    cfg2 = gnn.GNNArchitectureConfig(5, 2, [64, 64], [4], [5], initial_node_feature_embedding=True,
+                                     node_feature_embedding_layer_dimensions=[16, 64])
+    model2 = gnn.DetNetBasic(cfg2).to(DEV)
+    gcfg2 = GraphConstructionConfiguration("knn", {"k": 6}, ["rcs"], ["relative_position"], "directed", "X")
+    ei2, ea2, c3, bb3 = model2.forward_from_points(gcfg2, pos, vel, x, ptr)
+    for b in model2.batch_norms:
+        b.module.reset_running_stats()
+    c4, bb4 = model2(x, ei2, ea2)
+    assert mo.relative_error(c3, c4) <= 1e-5 and mo.relative_error(bb3, bb4) <= 1e-5
+
+
 def test_cpu_tensors_are_rejected(gnn):
     conv = gnn.MPNNConv(2, 4, 3)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
