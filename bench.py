@@ -144,8 +144,11 @@ def kernel_algorithmic_bytes(name: str, n: int, e: int, wl: dict):
     table = {
         # B rows (unique) + slot sources + slot edge attributes + row pointers + M rows
         "edge_aggregate": 4 * n * pp + 4 * e + 4 * de * e + 4 * (n + 1) + 4 * n * pp,
-        # fused aggregate + node update: B rows (unique) + slot sources / attributes / row pointers + x + h
-        "edge_update_fused": 4 * n * pp + 4 * e + 4 * de * e + 4 * (n + 1) + 4 * n * c + 4 * n * c,
+        # fused aggregate + node update: B main rows (unique) + slot sources / attributes / row pointers + reduced
+        # tail channels + x + h  (M' never exists in HBM)
+        "edge_update_fused": 4 * n * 2 * c + 4 * e + 4 * de * e + 4 * (n + 1) + 16 * n + 4 * n * c + 4 * n * c,
+        # tail channels of the messages: B tail rows + slot sources / attributes / row pointers + reduced rows
+        "edge_tail_reduce": 16 * n + 4 * e + 4 * de * e + 4 * (n + 1) + 16 * n,
         "node_gemm_pre": 4 * n * c + 4 * n * pp,             # read x, write B = x W_s^T
         "node_gemm_post": 4 * n * c + 4 * n * pp + 4 * n * c,  # read x and M, write h
         "linear_pre_node": 4 * n * c + 4 * n * pp,

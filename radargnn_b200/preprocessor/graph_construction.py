@@ -34,9 +34,15 @@ class GraphConstructor():
 
         if "time_index" in config.node_features:
             # rank of every timestamp among the sorted distinct values (dataset_creation.py:214-223)
+            # on the device (rgnn_time_index): sort + dense rank of the frame's timestamps; float64 holds the
+            # datasets' integer microsecond stamps exactly (< 2^53)
+            from .. import ops
             ts = np.asarray(point_cloud.timestamp)
-            _, inverse = np.unique(ts, return_inverse=True)
-            graph.add_invariant_feature("time_index", inverse.reshape(ts.shape).astype(ts.dtype))
+            if not torch.cuda.is_available():
+                raise RuntimeError("radargnn_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+            dev = torch.device("cuda", torch.cuda.current_device())
+            t_idx = ops.time_index(torch.from_numpy(ts.reshape(-1).astype(np.float64)).to(dev)).cpu().numpy()
+            graph.add_invariant_feature("time_index", t_idx.reshape(ts.shape).astype(ts.dtype))
 
         graph.build(distance_basis, config.graph_construction_algorithm, k=config.k, r=config.r)
         graph.extract_node_pair_features(config.edge_features, config.edge_mode)
@@ -60,6 +66,26 @@ class GraphData:
             if isinstance(v, torch.Tensor):
                 setattr(self, k, v.to(device))
         return self
+
+
+def collate_graph_data(graphs) -> GraphData:
+    """PyG's disjoint-union collate of a list of device-resident ``GraphData`` (what the reference's
+    ``DataLoader(graph_list, batch_size)`` does on the CPU for every step, utils/data_handling.py:25-30):
+    concatenation is memory plumbing (torch.cat), the node-id offsets of edge_index and the ``batch`` vector come
+    from ``rgnn_collate_offsets``.  Returns a GraphData with the extra attributes ``batch`` and ``ptr``."""
+    from .. import ops
+    if len(graphs) == 0:
+        raise ValueError("collate_graph_data needs at least one graph")
+    nodes = [int(g.x.shape[0]) for g in graphs]
+    edges = [int(g.edge_index.shape[1]) for g in graphs]
+    node_ptr = np.concatenate([[0], np.cumsum(nodes)]).astype(np.int64)
+    edge_ptr = np.concatenate([[0], np.cumsum(edges)]).astype(np.int64)
+    cat = lambda name: (None if getattr(graphs[0], name) is None else torch.cat([getattr(g, name) for g in graphs], dim=0))
+    edge_index = torch.cat([g.edge_index for g in graphs], dim=1).contiguous()
+    edge_index, batch = ops.collate_offsets(edge_index, edge_ptr, node_ptr)
+    out = GraphData(cat("x"), edge_index, cat("edge_attr"), cat("y"), cat("pos"), cat("vel"))
+    out.batch, out.ptr = batch, torch.from_numpy(node_ptr).to(batch.device)
+    return out
 
 
 def create_graph_data(graph: GeometricGraph, y: Optional[np.ndarray] = None) -> GraphData:

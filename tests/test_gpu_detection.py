@@ -137,3 +137,27 @@ def test_collate_offsets_match_disjoint_union(ops):
     ei, batch = ops.collate_offsets(torch.cat(parts, dim=1).contiguous().to(DEV), edge_ptr, node_ptr)
     assert torch.equal(ei.cpu(), want)
     assert batch.cpu().tolist() == [f for f, n in enumerate(nodes) for _ in range(n)]
+
+
+def test_collate_graph_data_equals_per_graph_forward(ops):
+    """Disjoint-union batching on the device: a layer on the collated batch == the layer on every graph."""
+    from radargnn_b200.preprocessor import GraphConstructionConfiguration, GraphConstructor, RadarPointCloud, collate_graph_data, create_graph_data
+    cfg_g = GraphConstructionConfiguration("knn", {"k": 5, "r": 1.0}, ["rcs", "time_index", "degree"], ["relative_position"], "directed", "X")
+    graphs = []
+    for s, n in enumerate([120, 40, 77]):
+        fr = synthetic.radar_frame(n, seed=s)
+        pc = RadarPointCloud()
+        pc.X_cc, pc.V_cc_compensated, pc.rcs, pc.timestamp = fr.X_cc, fr.V_cc_compensated, fr.rcs, fr.timestamp
+        g = GraphConstructor.build_geometric_graph(cfg_g, pc)
+        np.testing.assert_array_equal(g.F["time_index"].reshape(-1), do.time_index(np.asarray(fr.timestamp).reshape(-1)))
+        graphs.append(create_graph_data(g).to(DEV))
+    batch = collate_graph_data(graphs)
+    assert batch.x.shape[0] == 237 and batch.edge_index.shape[1] == 237 * 5
+    off = 0
+    for g in graphs:
+        m = g.x.shape[0]
+        sel = (batch.batch == graphs.index(g))
+        assert int(sel.sum()) == m
+        cols = (batch.edge_index[0] >= off) & (batch.edge_index[0] < off + m)
+        assert torch.equal(batch.edge_index[:, cols] - off, g.edge_index)
+        off += m
