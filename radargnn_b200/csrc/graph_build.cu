@@ -407,6 +407,129 @@ knn_query_kernel(const T* __restrict__ sorted_pts, const int32_t* __restrict__ s
   }
 }
 
+// ---- k-NN query with fp32 list keys -------------------------------------------------------------------
+// Same search, same results (ascending (fp64 squared distance, index), bit-exact against sklearn), but the
+// best-k list holds (float key, sorted position) instead of (double distance, point id): 2 registers per slot
+// instead of 3, and the 16-step insertion cascade -- what the kernel spends its time in, it runs for the whole
+// warp whenever ANY lane accepts a candidate -- compares with one FSETP per slot instead of two DSETP + ISETP +
+// predicate logic.  Rounding to fp32 is monotone, so key_a < key_b implies d_a < d_b; only candidates whose
+// keys are EQUAL need the exact comparison, and for those the fp64 distance of the list entry is recomputed
+// from its coordinates (rare: a handful per million insertions on continuous data, every time on duplicates).
+template <typename T, int DIMS, int KMAX, int OCC>
+__global__ void __launch_bounds__(128, OCC)
+knn_query_f32key_kernel(const T* __restrict__ sorted_pts, const int32_t* __restrict__ sorted_idx,
+                        const int32_t* __restrict__ sorted_cell, const int32_t* __restrict__ sorted_frame,
+                        const int32_t* __restrict__ cell_start, const FrameGrid* __restrict__ grids,
+                        int64_t n_points, int k, int64_t* __restrict__ edge_index, int64_t n_edges,
+                        int32_t* __restrict__ in_degree, const int32_t* __restrict__ degree_map) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= n_points) return;
+  const FrameGrid g = grids[sorted_frame[q]];
+  if (!g.active) return;
+  Point<T, DIMS> me;
+  me.load(sorted_pts + q * DIMS);
+  const int c = sorted_cell[q] - g.cell_off;
+  const int cy = c / g.gx, cx = c - cy * g.gx;
+
+  // DESCENDING list: slot 0 = current k-th (worst).  Empty slots: key +inf, position INT_MAX; slots >= k:
+  // key -inf (no candidate passes).
+  constexpr int kEmpty = 0x7fffffff;
+  float bf[KMAX];
+  int bp[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    bf[j] = j < k ? INFINITY : -INFINITY;
+    bp[j] = j < k ? kEmpty : -1;
+  }
+  // exact order of candidate (d, id) against the list entry at sorted position pj (equal fp32 keys only)
+  auto exact_beats = [&](double d, int id, int pj) -> bool {
+    if (pj == kEmpty) return true;
+    if (pj < 0) return false;
+    Point<T, DIMS> o;
+    o.load(sorted_pts + static_cast<int64_t>(pj) * DIMS);
+    return cand_less(d, id, rdist<DIMS>(me.v, o.v), sorted_idx[pj]);
+  };
+
+  const double slack = 1e-7 * g.h + 1e-14 * (fabs(me.v[0]) + fabs(me.v[1]) + fabs(g.x0) + fabs(g.y0));
+  const int max_ring = g.gx > g.gy ? g.gx : g.gy;
+  for (int r = 0; r <= max_ring; ++r) {
+    const int x0 = cx - r, x1 = cx + r, y0 = cy - r, y1 = cy + r;
+    const int n_spans = r == 0 ? 1 : 4 * r;
+    for (int s = 0; s < n_spans; ++s) {
+      int row, xa, xb;
+      if (s < 2) {
+        row = s == 0 ? y0 : y1;
+        xa = x0 < 0 ? 0 : x0;
+        xb = x1 >= g.gx ? g.gx - 1 : x1;
+        if (r == 0) { xa = cx; xb = cx; }
+      } else {
+        row = y0 + 1 + ((s - 2) >> 1);
+        xa = xb = ((s - 2) & 1) ? x1 : x0;
+        if (xa < 0 || xa >= g.gx) continue;
+      }
+      if (row < 0 || row >= g.gy) continue;
+      const int base = g.cell_off + row * g.gx;
+      const int p0 = cell_start[base + xa], p1 = cell_start[base + xb + 1];
+      for (int p = p0; p < p1; ++p) {
+        if (p == q) continue;  // self is excluded by index, never by distance
+        Point<T, DIMS> o;
+        o.load(sorted_pts + static_cast<int64_t>(p) * DIMS);
+        const double d = rdist<DIMS>(me.v, o.v);
+        const float df = __double2float_rn(d);
+        if (df <= bf[0]) {
+          bool take = df < bf[0];
+          if (!take) take = exact_beats(d, sorted_idx[p], bp[0]);   // equal keys with the k-th: exact order
+          if (take) {
+            bool prev = true, eq = false;   // prev: the candidate beats slot j; eq: some list key equals the candidate's
+#pragma unroll
+            for (int j = 0; j < KMAX - 1; ++j) {
+              const bool sh = df < bf[j + 1];  // slot j+1 moves down to j
+              eq = eq || (df == bf[j + 1]);
+              bf[j] = sh ? bf[j + 1] : (prev ? df : bf[j]);
+              bp[j] = sh ? bp[j + 1] : (prev ? p : bp[j]);
+              prev = sh;
+            }
+            if (prev) { bf[KMAX - 1] = df; bp[KMAX - 1] = p; }
+            if (eq) {
+              // the candidate sits below every entry with the same key: bubble it up past those it beats
+              const int id = sorted_idx[p];
+#pragma unroll
+              for (int j = 0; j < KMAX - 1; ++j) {
+                if (bp[j] == p && bf[j + 1] == df && exact_beats(d, id, bp[j + 1])) {
+                  bp[j] = bp[j + 1]; bp[j + 1] = p;   // keys are equal: only the positions swap
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    double gap = INFINITY;
+    if (x0 > 0) gap = fmin(gap, me.v[0] - (g.x0 + x0 * g.h));
+    if (x1 < g.gx - 1) gap = fmin(gap, (g.x0 + (x1 + 1) * g.h) - me.v[0]);
+    if (y0 > 0) gap = fmin(gap, me.v[1] - (g.y0 + y0 * g.h));
+    if (y1 < g.gy - 1) gap = fmin(gap, (g.y0 + (y1 + 1) * g.h) - me.v[1]);
+    if (gap == INFINITY) break;  // whole frame searched
+    gap -= slack;
+    // upper bound of the exact k-th distance: one fp32 ulp above its key
+    const double kth_ub = bf[0] < INFINITY ? static_cast<double>(__uint_as_float(__float_as_uint(bf[0]) + 1u)) : INFINITY;
+    if (gap > 0.0 && kth_ub < gap * gap) break;
+  }
+
+  const int i = sorted_idx[q];
+  const int64_t e0 = g.edge_off + (static_cast<int64_t>(i) - g.pt_begin) * k;
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    if (j < k) {  // slot j is the (k-1-j)-th nearest
+      const bool filled = static_cast<unsigned>(bp[j]) < static_cast<unsigned>(n_points);
+      const int nb = filled ? sorted_idx[bp[j]] : 0x7fffffff;   // a slot that never received a candidate keeps the sentinel
+      edge_index[e0 + (k - 1 - j)] = i;
+      edge_index[n_edges + e0 + (k - 1 - j)] = nb;
+      if (in_degree != nullptr && filled) atomicAdd(&in_degree[degree_map != nullptr ? degree_map[nb] : nb], 1);
+    }
+  }
+}
+
 // ---- radius query: count, then fill (rows ascending in j after sort_rows_kernel) -------------
 template <typename T, int DIMS, bool FILL>
 __global__ void __launch_bounds__(128)
@@ -563,7 +686,23 @@ int knn_query_t(int64_t n, int32_t k, int64_t* edge_index, int64_t n_edges, int3
   knn_query_kernel<T, DIMS, KMAX, OCC><<<blocks, 128, 0, stream>>>(pts, w.sorted_idx, w.sorted_cell,  \
       w.sorted_frame, w.cell_start, w.grids, n, k, edge_index, n_edges, in_degree, degree_map)
   static int occ16 = 0;   // RGNN_KNN_OCC = 4 | 6 | 8: experiments on the k <= 16 variant
-  if (occ16 == 0) { const char* e = getenv("RGNN_KNN_OCC"); occ16 = e != nullptr ? atoi(e) : 6; }
+  if (occ16 == 0) { const char* e = getenv("RGNN_KNN_OCC"); occ16 = e != nullptr ? atoi(e) : -1; }
+  static int keys = 0;    // RGNN_KNN_KEYS = 64: the fp64-key kernel (experiments / cross-check); default fp32 keys
+  if (keys == 0) { const char* e = getenv("RGNN_KNN_KEYS"); keys = (e != nullptr && atoi(e) == 64) ? 64 : 32; }
+  if (keys == 32) {
+#define RGNN_KNN32_LAUNCH(KMAX, OCC)                                                                         \
+  knn_query_f32key_kernel<T, DIMS, KMAX, OCC><<<blocks, 128, 0, stream>>>(pts, w.sorted_idx, w.sorted_cell,  \
+      w.sorted_frame, w.cell_start, w.grids, n, k, edge_index, n_edges, in_degree, degree_map)
+    if (k <= 4) RGNN_KNN32_LAUNCH(4, 8);
+    else if (k <= 8) RGNN_KNN32_LAUNCH(8, 8);
+    else if (k <= 16) { if (occ16 == 4) RGNN_KNN32_LAUNCH(16, 4); else if (occ16 == 8) RGNN_KNN32_LAUNCH(16, 8); else RGNN_KNN32_LAUNCH(16, 6); }   // 6: 78 registers, no spills (8: 64 + spills, measured equal)
+    else if (k <= 24) RGNN_KNN32_LAUNCH(24, 5);
+    else if (k <= 32) RGNN_KNN32_LAUNCH(32, 4);
+    else RGNN_KNN32_LAUNCH(64, 2);
+#undef RGNN_KNN32_LAUNCH
+    RGNN_LAUNCH_CHECK();
+    return RGNN_OK;
+  }
   if (k <= 4) RGNN_KNN_LAUNCH(4, 8);
   else if (k <= 8) RGNN_KNN_LAUNCH(8, 8);
   else if (k <= 16) { if (occ16 == 8) RGNN_KNN_LAUNCH(16, 8); else if (occ16 == 4) RGNN_KNN_LAUNCH(16, 4); else RGNN_KNN_LAUNCH(16, 6); }
