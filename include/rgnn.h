@@ -310,6 +310,21 @@ int rgnn_time_index(const double* timestamp, const int64_t* frame_ptr, const int
 int rgnn_collate_offsets(int64_t* edge_index, int64_t n_edges, const int64_t* edge_ptr, const int64_t* node_ptr, int32_t n_frames,
                          int64_t n_nodes, int64_t* batch_of_node, rgnn_stream_t stream);
 
+/* Graph-specific half of the backward of MPNNConv / RadarPointGNNConv with one Linear in pre_mlp (autograd through
+ * gnn/mpnn_layers.py:86-101, 171-184; gnn/trainer.py:228-231).  With m_e = A[t_e] + B[s_e] + W_e e_e + bias
+ * (A = x W_t^T or NULL for RadarPointGNNConv, B = x W_s^T, both [N, pp], pp = p rounded up to 4) and grad_m [N, ld_grad]
+ * the gradient of the aggregated messages, it returns
+ *   m_out [N, pp]     the aggregated messages themselves (0 for nodes without incoming edge),
+ *   grad_a [N, pp]    sum over a node's incoming edges of the per-edge message gradient (also the bias gradient, summed),
+ *   grad_b [N, pp]    the same sum over the node's outgoing edges (scatter by source),
+ *   grad_we [p, de]   gradient of W_e,   grad_ea_csc [E, de] gradient of the edge attributes in CSC slot order (may be NULL).
+ * max / min route every channel's gradient to the winning edge (first slot on exact ties), add to every edge, mean to
+ * every edge / deg.  grad_b, grad_we, grad_ea_csc are zeroed by the call and accumulated with fp32 atomics. */
+int rgnn_conv_backward_route(int32_t aggr, const float* a, const float* b, int32_t p, const float* bias, const float* w_e,
+                             int64_t ldwe, int32_t de, const float* ea_csc, const int32_t* csc_ptr, const int32_t* csc_src,
+                             int64_t n_nodes, int64_t n_edges, const float* grad_m, int64_t ld_grad, float* m_out, float* grad_a,
+                             float* grad_b, float* grad_we, float* grad_ea_csc, rgnn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------ */
 /* fused path: graph build + L-layer MPNN forward (the north-star hot path)               */
 /* ------------------------------------------------------------------------------------ */

@@ -130,6 +130,9 @@ _PROTOTYPES = {
     "rgnn_time_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "rgnn_collate_offsets": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
                                        C.c_void_p]),
+    "rgnn_conv_backward_route": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rgnn_pipeline_workspace_bytes": (C.c_size_t, [C.POINTER(PipelineDesc), C.c_int64, C.c_int32, C.c_int64]),
     "rgnn_pipeline_forward": (C.c_int, [C.POINTER(PipelineDesc), C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,

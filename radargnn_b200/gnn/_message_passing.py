@@ -1,7 +1,7 @@
 """Building blocks standing in for the PyG classes the reference subclasses / instantiates
 (``MessagePassing``, ``nn.dense.linear.Linear``, ``nn.BatchNorm``), with the same parameter
 names so that the reference's ``state_dict``s load, and with every forward routed to the CUDA
-kernels of librgnn_b200.so (forward only: autograd through the kernels is not implemented)."""
+kernels of librgnn_b200.so; gradients flow through the ``torch.autograd.Function``s of ``_autograd.py``."""
 from __future__ import annotations
 
 from collections import OrderedDict
@@ -20,8 +20,13 @@ class Linear(torch.nn.Linear):
         self.in_channels, self.out_channels = in_channels, out_channels
 
     def forward(self, x: torch.Tensor, relu_input: bool = False) -> torch.Tensor:
+        from ._autograd import LinearFunction, wants_grad
         lead = x.shape[:-1]
-        y = ops.linear(x.reshape(-1, x.shape[-1]), self.weight, self.bias, relu_input=relu_input)
+        x2 = x.reshape(-1, x.shape[-1])
+        if wants_grad(x2, self.weight, self.bias):
+            y = LinearFunction.apply(x2, self.weight, self.bias, relu_input)
+        else:
+            y = ops.linear(x2, self.weight, self.bias, relu_input=relu_input)
         return y.reshape(*lead, y.shape[-1])
 
 
@@ -44,9 +49,11 @@ class BatchNorm(torch.nn.Module):
             momentum = 0.1 if m.momentum is None else m.momentum
             if m.num_batches_tracked is not None and m.training:
                 m.num_batches_tracked += 1
-            return ops.batchnorm_relu(x, m.weight, m.bias, m.eps, momentum,
-                                      m.running_mean if m.training else None,
-                                      m.running_var if m.training else None, relu=relu)
+            from ._autograd import BatchNormReluFunction, wants_grad
+            rm, rv = (m.running_mean, m.running_var) if m.training else (None, None)
+            if wants_grad(x, m.weight, m.bias):
+                return BatchNormReluFunction.apply(x, m.weight, m.bias, m.eps, momentum, rm, rv, relu)
+            return ops.batchnorm_relu(x, m.weight, m.bias, m.eps, momentum, rm, rv, relu=relu)
         scale = torch.rsqrt(m.running_var + m.eps)
         beta = torch.zeros_like(scale)
         if m.weight is not None:

@@ -107,7 +107,13 @@ class MPNNConv(MessagePassing):
     def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor) -> Tensor:
         self._check_inputs(x, edge_index, edge_attr)
         csc = self.csc(edge_index, x.shape[0])
-        return ops.conv_forward(self.conv_params(), x, csc, edge_attr)
+        params = self.conv_params()
+        from ._autograd import ConvFunction, wants_grad
+        if len(params.pre) == 1 and len(params.post) == 1 and params.edge_encoder is None and \
+                wants_grad(x, edge_attr, *[t for pair in params.pre + params.post for t in pair]):
+            (w_pre, b_pre), (w_post, b_post) = params.pre[0], params.post[0]
+            return ConvFunction.apply(x, edge_attr, w_pre, b_pre, w_post, b_post, params, csc)
+        return ops.conv_forward(params, x, csc, edge_attr)
 
     def message(self, x_i: Tensor, x_j: Tensor, edge_attr: Tensor) -> Tensor:
         """Per-edge messages ``pre_mlp([x_i ; x_j ; e])`` (kept for API parity; ``forward`` does
@@ -165,7 +171,13 @@ class RadarPointGNNConv(MessagePassing):
     def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor) -> Tensor:
         self._check_inputs(x, edge_index, edge_attr)
         csc = self.csc(edge_index, x.shape[0])
-        return ops.conv_forward(self.conv_params(), x, csc, edge_attr)
+        params = self.conv_params()
+        from ._autograd import ConvFunction, wants_grad
+        if len(params.pre) == 1 and len(params.post) == 1 and params.edge_encoder is None and \
+                wants_grad(x, edge_attr, *[t for pair in params.pre + params.post for t in pair]):
+            (w_pre, b_pre), (w_post, b_post) = params.pre[0], params.post[0]
+            return ConvFunction.apply(x, edge_attr, w_pre, b_pre, w_post, b_post, params, csc)
+        return ops.conv_forward(params, x, csc, edge_attr)
 
     def message(self, x_i: Tensor, x_j: Tensor, edge_attr: Tensor) -> Tensor:
         m = torch.cat([x_j, edge_attr], dim=-1)

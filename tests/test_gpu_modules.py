@@ -158,7 +158,7 @@ def test_get_mlp(gnn):
     _ones(mlp)
     x = torch.tensor([1, 1], dtype=torch.float32, device=DEV)
     assert mlp[0].weight.shape == (5, 2) and mlp[2].weight.shape == (3, 5)
-    assert (mlp(x).cpu().numpy() == np.array([10, 10, 10])).all()
+    assert (mlp(x).detach().cpu().numpy() == np.array([10, 10, 10])).all()   # reference test_gnn.py:23 detaches too
 
 
 def test_det_net_basic_layer_types(gnn):
@@ -191,7 +191,7 @@ def test_mpnn_conv_structure_and_forward(gnn):
     ei = torch.tensor([[0, 1, 0], [1, 0, 1]], device=DEV)
     ea = torch.tensor([[3, 3, 3], [4, 4, 4], [1, 1, 1]], dtype=torch.float32, device=DEV)
     out = conv.forward(x, ei, ea)
-    assert (out[1, :].cpu().numpy() == 436).all()
+    assert (out[1, :].detach().cpu().numpy() == 436).all()
     # message() keeps the reference semantics: pre_mlp([x_i ; x_j ; e])
     m = conv.message(x[ei[1]], x[ei[0]], ea)
     assert m[0].cpu().tolist() == [15.0] * 7
