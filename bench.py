@@ -579,8 +579,24 @@ def main_gpu(args, wl):
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Teardown must not be able to hang the launcher (the 2-GPU run of this round printed its line and then sat
+        # in the communicator's destruction while the CUDA graph holding the captured NCCL all-reduce was still
+        # alive): drop the graph first, synchronise, and keep a watchdog that ends the process if NCCL still blocks.
+        import gc
+        import threading
+        torch.cuda.synchronize()
+        step_device = step_eager = None   # noqa: F841 (closures over the graph)
+        graph = None                      # noqa: F841
+        gc.collect()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
         dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+        watchdog.cancel()
     return 0
 
 
