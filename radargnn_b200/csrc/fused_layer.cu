@@ -232,11 +232,17 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
     // =========================== aggregate warps ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kAggRegs));
     const int q = lane & 7, quarter = lane >> 3;
-    float4 w[DE][4];
+    // edge weights of the lane's 16 channels: in registers for De <= 2 (32 registers); wider edge attributes would
+    // spill at 144 registers (De = 4: 64 registers, 1 KB of spills, 2x the time per edge), so their weights are read
+    // from shared memory one attribute at a time (4 LDS.128 per attribute and slot group)
+    constexpr bool kWeightsInRegs = DE <= 2;
+    float4 w[kWeightsInRegs ? DE : 1][4];
+    if (kWeightsInRegs) {
 #pragma unroll
-    for (int d = 0; d < DE; ++d)
+      for (int d = 0; d < DE; ++d)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) w[d][i] = ld4(&s.ws[d * kMain + 32 * i + 4 * q]);
+        for (int i = 0; i < 4; ++i) w[d][i] = ld4(&s.ws[d * kMain + 32 * i + 4 * q]);
+    }
     constexpr float kInit = MODE == RGNN_AGGR_MAX ? -INFINITY : (MODE == RGNN_AGGR_MIN ? INFINITY : 0.f);
     const float4 init4 = make_float4(kInit, kInit, kInit, kInit);
     constexpr bool kOrderFree = MODE == RGNN_AGGR_MAX || MODE == RGNN_AGGR_MIN;
@@ -319,13 +325,28 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
               for (int i = 0; i < 4; ++i) v[u][i] = on ? ld4(rp + 32 * i) : init4;
             }
           }
+          if (kWeightsInRegs) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+              for (int d = 0; d < DE; ++d) {
+                const float ed = __shfl_sync(0xffffffffu, ereg[d], l0 + u, 8);   // 0 for slots beyond the row's degree
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[u][i] = fma4x2(ed, w[d][i], v[u][i]);
+              }
+            }
+          } else {
 #pragma unroll
             for (int d = 0; d < DE; ++d) {
-              const float ed = __shfl_sync(0xffffffffu, ereg[d], l0 + u, 8);   // 0 for slots beyond the row's degree
+              float4 wd[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) v[u][i] = fma4x2(ed, w[d][i], v[u][i]);
+              for (int i = 0; i < 4; ++i) wd[i] = ld4(&s.ws[d * kMain + 32 * i + 4 * q]);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float ed = __shfl_sync(0xffffffffu, ereg[d], l0 + u, 8);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[u][i] = fma4x2(ed, wd[i], v[u][i]);
+              }
             }
           }
 #pragma unroll
