@@ -56,6 +56,7 @@ constexpr int kStageFloats = 32 * 36;                       // per tile warp: tr
 constexpr int kHold = 4;                                    // slots held per lane: a quarter-warp holds 32 slots of its row
 // register split (setmaxnreg): 3 aggregate warpgroups + 1 tile warpgroup share 4 x 128 registers per thread slot
 constexpr int kAggRegs = 144, kTileRegs = 80;
+constexpr int kLastTileFullDefault = 1;                     // see vbeg in the kernel
 constexpr uint32_t kXCol = 128, kMCol = 256;                // TMEM columns: accumulator 0.., x stages, M' stages
 
 struct FusedParams {
@@ -72,6 +73,7 @@ struct FusedParams {
   int32_t* status;
   int32_t n_nodes, rows_per_cta, tiles_per_cta;
   long long* trace; int32_t trace_cta;   // debug timeline of one CTA (scripts/trace_fused.py)
+  int32_t last_tile_full;                // tile layout: 1 = the partial tile comes first (RGNN_FUSED_LAST_TILE_FULL)
 };
 
 struct FusedSmem {
@@ -225,6 +227,10 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
   if (p.trace != nullptr && blockIdx.x == p.trace_cta && tid == 0) p.trace[1000] = clock64();
   const int row_begin = blockIdx.x * p.rows_per_cta;
   const int row_end = min(p.n_nodes, row_begin + p.rows_per_cta);
+  // Tiles are laid so that the LAST one ends at row_end and the FIRST one is the partial one (its rows below row_begin
+  // are dead): when the aggregate warps finish, the tile warps have a full tile's production time behind them and only
+  // the last quarter's conversion, the MMAs and one epilogue remain exposed (a short last tile left ~1.5 tiles).
+  const int vbeg = p.last_tile_full ? row_end - p.tiles_per_cta * kRows : row_begin;   // may be negative: every access checks row >= row_begin
   const int tiles = p.tiles_per_cta;
   bool timed_out = false;
 
@@ -249,13 +255,13 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
     const float* bcol = p.bm + 4 * q;
     const int units = tiles * 32;                                  // 4-row units of this CTA (whole tiles)
     const int kPasses = (units + kAggWarps - 1) / kAggWarps;
-    const int row_base = row_begin + warp * 4 + quarter;
+    const int row_base = vbeg + warp * 4 + quarter;
 
     // software pipeline over the passes: row pointers two passes ahead, the first 32 slot sources one pass ahead
     auto load_ptr = [&](int pass, int& beg, int& deg) {
       const int row = row_base + pass * kPassRows;
       beg = 0; deg = 0;
-      if (pass < kPasses && row < row_end) { beg = p.csc_ptr[row]; deg = p.csc_ptr[row + 1] - beg; }
+      if (pass < kPasses && row >= row_begin && row < row_end) { beg = p.csc_ptr[row]; deg = p.csc_ptr[row + 1] - beg; }
     };
     auto load_src = [&](int beg, int deg, int b, int (&src)[kHold]) {
 #pragma unroll
@@ -281,7 +287,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
       long long* tr = (p.trace != nullptr && blockIdx.x == p.trace_cta && lane == 0 && it < 24) ? p.trace + 64 + warp * 48 + it * 2 : nullptr;
       if (tr != nullptr) tr[0] = clock64();
       const int row = row_base + it * kPassRows;
-      const bool live = row < row_end;
+      const bool live = row >= row_begin && row < row_end;
       load_ptr(it + 2, beg2, deg2);
       int cur_src[kHold];
       float cur_e[kHold][DE];
@@ -431,8 +437,8 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
     // the x rows of a tile are pulled into L2 two tiles ahead (a row = two 128-byte lines), so that the loads of
     // step (1) are L2 hits: a shared-memory staging buffer would take 32 KB away from the L1 the gathers live on
     auto prefetch_x = [&](int t) {
-      const int row = row_begin + t * kRows + tt;
-      if (t < tiles && row < row_end) {
+      const int row = vbeg + t * kRows + tt;
+      if (t < tiles && row >= row_begin && row < row_end) {
         const float* xr = p.x + (p.x_rows != nullptr ? static_cast<int64_t>(p.x_rows[row]) : row) * p.ldx;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(xr));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + 32));
@@ -447,14 +453,14 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
     // fetched one tile ahead.
     const int pt = p.p - kMain;                   // tail channels (1..4)
     auto load_tail = [&](int t) {
-      const int row = row_begin + t * kRows + tt;
-      return (t < tiles && row < row_end) ? ld4(p.mt + static_cast<int64_t>(row) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int row = vbeg + t * kRows + tt;
+      return (t < tiles && row >= row_begin && row < row_end) ? ld4(p.mt + static_cast<int64_t>(row) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     float4 mt4 = load_tail(0);
 
     for (int t = 0; t < tiles; ++t) {
-      const int row = row_begin + t * kRows + tt;
-      const bool row_ok = row < row_end;
+      const int row = vbeg + t * kRows + tt;
+      const bool row_ok = row >= row_begin && row < row_end;
       const uint32_t par = static_cast<uint32_t>(t) & 1u;
       long long* tr = (p.trace != nullptr && blockIdx.x == p.trace_cta && tt == 0 && t < 8) ? p.trace + t * 8 : nullptr;
       if (tr != nullptr) tr[0] = clock64();
@@ -530,7 +536,8 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
       if (!mbar_wait(acc_full, par)) timed_out = true;
       if (tr != nullptr) tr[6] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int tile_row0 = row_begin + t * kRows + qd * 32;
+      const int tile_row0 = vbeg + t * kRows + qd * 32;
+      const int rows_first = max(0, row_begin - tile_row0);          // rows of the quarter below the CTA's range
       const int rows_valid = max(0, min(32, row_end - tile_row0));
       const int c4 = lane & 7, rsub = lane >> 3;
       for (int cd = 0; cd * 2 < n_blocks; ++cd) {
@@ -564,7 +571,7 @@ fused_layer_kernel(const __grid_constant__ FusedParams p) {
           const float* srow = st + rsub * 36 + c4 * 4;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            if (it * 4 + rsub < rows_valid) {
+            if (it * 4 + rsub >= rows_first && it * 4 + rsub < rows_valid) {
               const float4 v4 = ld4(srow + it * (4 * 36));
               *reinterpret_cast<float4*>(dst + static_cast<int64_t>(it) * 4 * p.ldy) = v4;
               csum4.x += v4.x; csum4.y += v4.y; csum4.z += v4.z; csum4.w += v4.w;
@@ -790,6 +797,10 @@ int launch_fused_layer(const FusedLayerArgs& a, cudaStream_t stream) {
   const int grid = static_cast<int>(div_up(a.n_nodes, p.rows_per_cta));
   p.n_partials = grid;
   p.trace = g_fused_trace; p.trace_cta = g_fused_trace_cta; g_fused_trace = nullptr;
+  {
+    const char* e = getenv("RGNN_FUSED_LAST_TILE_FULL");   // read per launch: scripts compare the two layouts in one process
+    p.last_tile_full = (e != nullptr) ? (e[0] == '1' ? 1 : 0) : kLastTileFullDefault;
+  }
   {
     RGNN_PROFILE("edge_tail_reduce", stream);
     int st = RGNN_ERR_UNSUPPORTED;
