@@ -176,6 +176,31 @@ def mpnn_fixtures():
         _save_module_case(name, model, x, ei, ea, out, dict(kind="DetNetBasic", **meta))
 
 
+def detection_fixtures():
+    """Loss: the arithmetic of the reference's gnn/trainer.py:184-216 executed as written (torch CrossEntropyLoss with
+    class weights + the per-node Python loop over torch HuberLoss; oracle/detection_oracle.detection_loss is those
+    lines).  NMS: torchvision.ops.nms itself, the function postprocessing.py:408 calls, after the reference's shift of
+    negative coordinates (:400-404)."""
+    import torch
+    import torchvision
+    from oracle import detection_oracle as do
+    g = torch.Generator().manual_seed(11)
+    n, k, nb = 600, 6, 5
+    cls, bb = torch.randn(n, k, generator=g) * 2, torch.randn(n, nb, generator=g) * 3
+    y = torch.cat([torch.randint(0, k, (n, 1), generator=g).float(), torch.randn(n, nb, generator=g) * 3], dim=1)
+    w = torch.rand(k, generator=g) + 0.5
+    loss, loss_cls, loss_bb, num_bb = do.detection_loss(cls, bb, y, w, bg_index=5, alpha=0.75, beta=1.25)
+    np.savez(os.path.join(GOLDEN_DIR, "detection_loss.npz"), cls=cls.numpy(), bb=bb.numpy(), y=y.numpy(), weight=w.numpy(),
+             bg_index=5, alpha=0.75, beta=1.25, loss=loss, loss_cls=loss_cls, loss_bb=loss_bb, num_bb=num_bb)
+    xy = torch.rand(400, 2, generator=g) * 40 - 10
+    wh = torch.rand(400, 2, generator=g) * 7 + 0.1
+    boxes = torch.cat([xy, xy + wh], dim=1)
+    scores = torch.rand(400, generator=g)
+    shift = abs(float(boxes.min())) + 100 if float(boxes.min()) < 0 else 0
+    keeps = {f"keep_{int(t * 100)}": torchvision.ops.nms((boxes + shift).float(), scores.float(), t).numpy() for t in (0.1, 0.3, 0.6)}
+    np.savez(os.path.join(GOLDEN_DIR, "nms_aligned.npz"), boxes=boxes.numpy(), scores=scores.numpy(), **keeps)
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     small = synthetic.radar_frame(n=48, seed=1, extent=(30.0, 30.0))
@@ -198,6 +223,7 @@ def main():
     graph_fixture("graph_radius4_tiny_brute", tiny, "radius", None, 4.0, ["degree"], ["relative_velocity"], "undirected", "X")
     ppf_pairs_fixture()
     mpnn_fixtures()
+    detection_fixtures()
 
 
 if __name__ == "__main__":

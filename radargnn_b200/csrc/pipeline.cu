@@ -4,6 +4,8 @@
 // (preprocessor/radarscenes/dataset_creation.py:187-229 -> gnn/gnn_models.py:124-128).
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "conv.cuh"
 #include "csc.cuh"
 #include "features.cuh"
@@ -322,6 +324,9 @@ int rgnn_pipeline_forward_host(const rgnn_pipeline_desc* desc, const float* pos_
   // builds the graph, and edge_index / edge_attr travel back while the layers run.  The whole sequence
   // (copies, ~40 kernels, cross-stream events) is captured into a CUDA graph the first time it is seen and
   // replayed while the arguments stay the same: the eager launches cost ~0.1 ms of host time per call.
+  // one call at a time per process: the per-device streams, events and the cached graph are shared state
+  static std::mutex host_path_mutex;
+  std::lock_guard<std::mutex> host_path_lock(host_path_mutex);
   HostPathStreams* hs = host_path_streams();
   if (hs == nullptr) return RGNN_ERR_CUDA;
   cudaStream_t ms = hs->main;

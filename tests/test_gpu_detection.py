@@ -161,3 +161,18 @@ def test_collate_graph_data_equals_per_graph_forward(ops):
         cols = (batch.edge_index[0] >= off) & (batch.edge_index[0] < off + m)
         assert torch.equal(batch.edge_index[:, cols] - off, g.edge_index)
         off += m
+
+
+def test_detection_kernels_match_committed_golden_fixtures(ops):
+    """The CUDA loss against the trainer's arithmetic, the CUDA NMS against torchvision.ops.nms (tests/golden/*.npz)."""
+    import os
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    d = np.load(os.path.join(gdir, "detection_loss.npz"))
+    out = ops.detection_loss(torch.from_numpy(d["cls"]).to(DEV), torch.from_numpy(d["bb"]).to(DEV), torch.from_numpy(d["y"]).to(DEV),
+                             torch.from_numpy(d["weight"]).to(DEV), int(d["bg_index"]), float(d["alpha"]), float(d["beta"])).cpu().numpy()
+    np.testing.assert_allclose(out[:3], [float(d["loss"]), float(d["loss_cls"]), float(d["loss_bb"])], rtol=2e-6)
+    assert out[3] == int(d["num_bb"])
+    m = np.load(os.path.join(gdir, "nms_aligned.npz"))
+    for t in (10, 30, 60):
+        got = ops.nms(torch.from_numpy(m["boxes"]).to(DEV), torch.from_numpy(m["scores"]).to(DEV), t / 100).cpu().numpy()
+        np.testing.assert_array_equal(got, m[f"keep_{t}"])

@@ -62,3 +62,20 @@ def test_iou_rotated_against_axis_aligned_and_identity():
 def test_time_index_is_dense_rank():
     ts = np.array([5.0, 1.0, 5.0, 3.0, 1.0, 9.0])
     np.testing.assert_array_equal(do.time_index(ts), [2, 0, 2, 1, 0, 3])
+
+
+def _golden(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+
+
+def test_oracle_matches_committed_golden_fixtures():
+    """tests/golden/detection_loss.npz / nms_aligned.npz (oracle/make_golden.py::detection_fixtures: the trainer's loss
+    arithmetic as written, torchvision.ops.nms itself)."""
+    d = _golden("detection_loss.npz")
+    got = do.detection_loss(torch.from_numpy(d["cls"]), torch.from_numpy(d["bb"]), torch.from_numpy(d["y"]),
+                            torch.from_numpy(d["weight"]), int(d["bg_index"]), float(d["alpha"]), float(d["beta"]))
+    assert got[0] == pytest.approx(float(d["loss"]), rel=1e-6) and got[3] == int(d["num_bb"])
+    m = _golden("nms_aligned.npz")
+    for t in (10, 30, 60):
+        np.testing.assert_array_equal(do.nms_aligned(m["boxes"], m["scores"], t / 100), m[f"keep_{t}"])
