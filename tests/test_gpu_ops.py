@@ -554,3 +554,22 @@ def test_host_entry_point_replays_its_graph(ops):
     assert not torch.equal(c, a)
     d = rerun(two)
     torch.testing.assert_close(d, device_path(two), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("aggr", ["max", "mean", "min"])
+def test_fused_layer_degenerate_sizes(ops, aggr):
+    """Fused aggregate + update kernel (C = 64 MPNNConv) on degenerate graphs: a single node, no edges at all, fewer
+    rows than one 4-row unit, one row past a tile boundary, an in-degree of 100 per node."""
+    g = torch.Generator().manual_seed(0)
+    c, de = 64, 2
+    p = 2 * c + de
+    params = {"pre_mlp.0.weight": torch.randn(p, p, generator=g) / p ** 0.5, "pre_mlp.0.bias": torch.randn(p, generator=g) * 0.1,
+              "post_mlp.0.weight": torch.randn(c, p + c, generator=g) / (p + c) ** 0.5, "post_mlp.0.bias": torch.randn(c, generator=g) * 0.1}
+    cp = _conv_params(ops, params, {"kind": "MPNNConv", "aggr": aggr})
+    for n, e in ((1, 0), (1, 3), (3, 0), (2, 5), (17, 40), (129, 1000), (4097, 9), (300, 30000)):
+        x = torch.randn(n, c, generator=g)
+        ei = torch.randint(0, n, (2, e), generator=g)
+        ea = torch.randn(e, de, generator=g)
+        want = mo.mpnn_conv_forward(params, x, ei, ea, aggr, dtype=torch.float64)
+        got = ops.conv_forward(cp, x.to(DEV), ops.csc_build(ei.to(DEV), n), ea.to(DEV)).cpu()
+        assert mo.relative_error(got, want) <= 2e-5 and torch.isfinite(got).all(), (n, e)
