@@ -132,7 +132,7 @@ init_tables_kernel(const __grid_constant__ FrameTableChunk c, int first, int cou
 __global__ void frame_grid_kernel(const long long* __restrict__ bbox, const int64_t* __restrict__ frame_ptr,
                                   const int64_t* __restrict__ frame_edge_off,
                                   const int32_t* __restrict__ frame_cell_off, int n_frames,
-                                  FrameGrid* __restrict__ grids) {
+                                  FrameGrid* __restrict__ grids, double points_per_cell) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= n_frames) return;
   FrameGrid g;
@@ -151,7 +151,7 @@ __global__ void frame_grid_kernel(const long long* __restrict__ bbox, const int6
   const double mnx = ordered_to_double(bbox[f * 4 + 0]), mny = ordered_to_double(bbox[f * 4 + 1]);
   const double mxx = ordered_to_double(bbox[f * 4 + 2]), mxy = ordered_to_double(bbox[f * 4 + 3]);
   const double w = mxx - mnx, hgt = mxy - mny;
-  double target = static_cast<double>(nf) / kPointsPerCell;
+  double target = static_cast<double>(nf) / points_per_cell;
   if (target < 1.0) target = 1.0;
   double h;
   if (!(w > 0.0) && !(hgt > 0.0)) h = 1.0;
@@ -654,8 +654,14 @@ int build_cell_lists_t(const T* basis, int32_t dims, const int64_t* frame_ptr_ho
   const unsigned blocks = div_up(n, kThreads);
   frame_bbox_kernel<T><<<blocks, kThreads, 0, stream>>>(basis, dims, n, w.frame_ptr, n_frames, w.bbox, status);
   RGNN_LAUNCH_CHECK();
+  static double points_per_cell = 0.0;   // RGNN_CELL_POINTS: experiments on the grid's target occupancy (>= 2: the cell array holds 2 N / 4 cells)
+  if (points_per_cell == 0.0) {
+    const char* e = getenv("RGNN_CELL_POINTS");
+    points_per_cell = e != nullptr ? atof(e) : static_cast<double>(kPointsPerCell);
+    if (!(points_per_cell >= 2.0)) points_per_cell = kPointsPerCell;
+  }
   frame_grid_kernel<<<div_up(n_frames, 64), 64, 0, stream>>>(w.bbox, w.frame_ptr, w.frame_edge_off,
-                                                             w.frame_cell_off, n_frames, w.grids);
+                                                             w.frame_cell_off, n_frames, w.grids, points_per_cell);
   RGNN_LAUNCH_CHECK();
   bin_count_kernel<T><<<blocks, kThreads, 0, stream>>>(basis, dims, n, w.frame_ptr, n_frames, w.grids,
                                                        w.point_cell, w.cell_count);
