@@ -137,9 +137,11 @@ def test_reference_import_paths_resolve_to_the_cuda_backed_classes():
         "from gnnradarobjectdetection.preprocessor.radar_point_cloud import RadarPointCloud\n"
         "from gnnradarobjectdetection.preprocessor.radarscenes.dataset_creation import GraphConstructor, create_graph_data\n"
         "from gnnradarobjectdetection.preprocessor.nuscenes.conversion import build_geometric_graph\n"
+        "from gnnradarobjectdetection.postprocessor.postprocessing import BoxSuppressor\n"
         "import radargnn_b200.gnn.mpnn_layers as impl, radargnn_b200.ops as ops\n"
         "assert MPNNConv is impl.MPNNConv and RadarPointGNNConv is impl.RadarPointGNNConv\n"
         "import inspect; assert 'ops.conv_forward' in inspect.getsource(MPNNConv.forward)\n"
+        "assert 'ops.nms' in inspect.getsource(BoxSuppressor.keep_indices)\n"
         "print('ok')\n") % os.path.join(root, "src")
     # run from another directory: the package must find radargnn_b200 by itself
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
