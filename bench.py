@@ -10,9 +10,11 @@ only all-reduce the loss scalar (NCCL).  One JSON line is printed by rank 0:
 
   value        whole-job edges/s with the inputs already resident in HBM (CUDA-event timed, L2 flushed
                between steps, max over ranks);
-  e2e          the same metric through the host-buffer C-ABI entry point (rgnn_pipeline_forward_host):
-               H2D of pos / vel / x0 from pinned memory and D2H of EVERY output of the path (edge_index,
-               edge_attr and the node embeddings) inside the timed region;  e2e_embeddings_only: the same call
+  e2e          the same metric through the host-buffer C-ABI entry point as submit + wait with two batches in
+               flight (rgnn_pipeline_submit_host / rgnn_pipeline_wait_host): H2D of pos / vel / x0 from pinned
+               memory and D2H of EVERY output of the path (edge_index, edge_attr and the node embeddings) of every
+               batch inside the timed region;  e2e_sync: one synchronous call per batch
+               (rgnn_pipeline_forward_host), the latency figure;  e2e_embeddings_only: the synchronous call
                downloading only the node embeddings (the graph stays on the device);
   roofline     dominant kernel: algorithmic bytes per launch / measured device time per launch, against
                MEASURED_PEAKS.json:hbm_gbs;  path_roofline: the whole step against SURVEY.md 8(d)'s B_alg;
@@ -512,9 +514,42 @@ def main_gpu(args, wl):
                 all_reduce_loss()   # persistent device scalars: no allocation, no host sync per step
         return step_host
 
+    # the same entry point as submit + wait with two batches in flight (rgnn_pipeline_submit_host): batch i + 1
+    # uploads and batch i - 1 downloads while batch i computes.  Each slot has its own pinned outputs and workspace;
+    # the L2 flush sits on the caller's stream in front of every submit, INSIDE the timed region.
+    depth = max(1, min(int(os.environ.get("RGNN_BENCH_E2E_DEPTH", "2")), _lib.HOST_SLOTS))
+    slots = []
+    for _ in range(depth):
+        slots.append({"h": torch.empty((n, c_last), dtype=torch.float32).pin_memory(),
+                      "ei": torch.empty((2, n_edges), dtype=torch.int64).pin_memory(),
+                      "ea": torch.empty((n_edges, handle.edge_dim), dtype=torch.float32).pin_memory(),
+                      "ws": _lib.workspace(host_ws.numel(), dev)})
+
+    def run_pipelined(steps: int) -> float:
+        """Device-clock time of `steps` batches through submit / wait, every batch's copies and the drain included."""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record(stream)
+        for i in range(steps):
+            sl = slots[i % depth]
+            if i >= depth:
+                _lib.check(lib.rgnn_pipeline_wait_host(i % depth))
+            flush.zero_()
+            _lib.check(lib.rgnn_pipeline_submit_host(
+                i % depth, C.byref(handle.desc), pos_h.data_ptr(), vel_h.data_ptr(), x0_h.data_ptr(), wl["c0"],
+                ptr.ctypes.data, n_frames, sl["ei"].data_ptr(), n_edges, sl["ea"].data_ptr(), sl["h"].data_ptr(),
+                sl["ws"].data_ptr(), sl["ws"].numel(), sp))
+            if world > 1:
+                all_reduce_loss()
+        for i in range(max(0, steps - depth), steps):
+            _lib.check(lib.rgnn_pipeline_wait_host(i % depth))
+        b.record(stream)       # the host has every batch's outputs by now: the event closes the region on the device clock
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3
+
     e2e_steps = max(3, min(args.steps, 20))
     e2e = {}
-    for key, full in (("e2e", True), ("e2e_embeddings_only", False)):
+    for key, full in (("e2e_sync", True), ("e2e_embeddings_only", False)):
         fn = make_step_host(full)
         for _ in range(3):
             fn()
@@ -522,11 +557,24 @@ def main_gpu(args, wl):
         t = max_over_ranks(timed(fn, e2e_steps))
         barrier()
         d2h = int(h_host.numel() * 4 + (ei_host.numel() * 8 + ea_host.numel() * 4 if full else 0))
+        if full:
+            h_host_full = h_host.clone()
         e2e[key] = {"value": n_edges * world * e2e_steps / t, "unit": "edges/s",
                     "h2d_bytes_per_step": int(pos_h.numel() * 4 + vel_h.numel() * 4 + x0_h.numel() * 4),
                     "d2h_bytes_per_step": d2h, "ms_per_step": t / e2e_steps * 1e3,
                     "api": "rgnn_pipeline_forward_host (pinned host buffers)",
                     "outputs": "edge_index + edge_attr + node embeddings" if full else "node embeddings"}
+
+    run_pipelined(4)
+    barrier()
+    t = max_over_ranks(run_pipelined(e2e_steps))
+    barrier()
+    for sl in slots:     # the pipelined batches carry the bytes of the synchronous call
+        assert torch.equal(sl["h"], h_host_full) and torch.equal(sl["ei"], ei_host), "pipelined host path differs"
+    e2e["e2e"] = dict(e2e["e2e_sync"], value=n_edges * world * e2e_steps / t, ms_per_step=t / e2e_steps * 1e3,
+                      api="rgnn_pipeline_submit_host / rgnn_pipeline_wait_host (pinned host buffers), "
+                          f"{depth} batches in flight, L2 flush inside the timed region",
+                      batches_in_flight=depth, sync_call_ms_per_step=e2e["e2e_sync"]["ms_per_step"])
 
     # ---- roofline of the dominant kernel: per-kernel CUDA events over the same steps ----------------
     _lib.profile_reset()
@@ -588,7 +636,7 @@ def main_gpu(args, wl):
             "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (graph build in f64)", "data": "synthetic",
             "config": config,
-            "e2e": e2e["e2e"], "e2e_embeddings_only": e2e["e2e_embeddings_only"],
+            "e2e": e2e["e2e"], "e2e_sync": e2e["e2e_sync"], "e2e_embeddings_only": e2e["e2e_embeddings_only"],
             "gpu_launches": int(launches),
             "roofline": roofline,
             "path_roofline": {"algorithmic_bytes_per_step": b_alg, "achieved": b_alg / step_s / 1e9, "peak": peak_gbs,

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RGNN_ABI_VERSION 3
+#define RGNN_ABI_VERSION 4
 
 typedef void* rgnn_stream_t; /* cudaStream_t */
 
@@ -373,6 +373,25 @@ int rgnn_pipeline_forward_host(const rgnn_pipeline_desc* desc, const float* pos_
                                int64_t* edge_index_host, int64_t n_edges, float* edge_attr_host,
                                float* h_host, void* workspace, size_t workspace_bytes,
                                rgnn_stream_t stream);
+
+/* The same call split into submit and wait, so that consecutive batches form a pipeline (the role of the
+ * prefetching DataLoader in front of the reference's loop, gnn/trainer.py:210-233): while batch i computes,
+ * batch i + 1 uploads and batch i - 1 downloads.  rgnn_pipeline_submit_host enqueues the work of one batch
+ * on `slot` (0 .. RGNN_HOST_SLOTS - 1) and returns without waiting; rgnn_pipeline_wait_host blocks until
+ * that batch's outputs are in the host buffers and returns its status (the error codes of
+ * rgnn_pipeline_forward_host).  Every slot in flight needs its own workspace and its own output buffers;
+ * the input buffers must stay untouched until the wait.  Batches compute in submission order (BatchNorm
+ * running statistics see them in that order).  Submitting to a slot that has not been waited for returns
+ * RGNN_ERR_INVALID_ARGUMENT, and so does waiting on an idle slot.  Pinned host buffers are needed for the
+ * copies to overlap. */
+#define RGNN_HOST_SLOTS 4
+int rgnn_pipeline_submit_host(int32_t slot, const rgnn_pipeline_desc* desc, const float* pos_host,
+                              const float* vel_host, const float* x0_host, int32_t c0,
+                              const int64_t* frame_ptr_host, int32_t n_frames,
+                              int64_t* edge_index_host, int64_t n_edges, float* edge_attr_host,
+                              float* h_host, void* workspace, size_t workspace_bytes,
+                              rgnn_stream_t stream);
+int rgnn_pipeline_wait_host(int32_t slot);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "librgnn_b200.so")
 OK, ERR_INVALID_ARGUMENT, ERR_K_NOT_SMALLER_THAN_N, ERR_WORKSPACE_TOO_SMALL, ERR_CUDA, \
     ERR_DOT_PRODUCT, ERR_INVALID_FEATURE, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_NON_FINITE_INPUT, \
     ERR_INDEX_OUT_OF_RANGE = range(11)
-ABI_VERSION = 3
+ABI_VERSION = 4
+HOST_SLOTS = 4   # RGNN_HOST_SLOTS
 F32, F64 = 0, 1
 DIRECTED, UNDIRECTED = 0, 1
 EDGE_FEATURES = {
@@ -142,6 +143,10 @@ _PROTOTYPES = {
     "rgnn_pipeline_forward_host": (C.c_int, [C.POINTER(PipelineDesc), C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rgnn_pipeline_submit_host": (C.c_int, [C.c_int32, C.POINTER(PipelineDesc), C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rgnn_pipeline_wait_host": (C.c_int, [C.c_int32]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

@@ -122,6 +122,55 @@ HostPathStreams* host_path_streams() {
   return &h;
 }
 
+// The pipelined host-buffer path (rgnn_pipeline_submit_host / rgnn_pipeline_wait_host): one upload, one compute
+// and one download stream per device, shared by every slot, so that consecutive calls form a software pipeline --
+// the upload of call i + 1 and the download of call i - 1 travel while call i computes (PCIe is full duplex), and
+// the compute of consecutive calls stays in submission order (BatchNorm running statistics are updated in that
+// order).  The two halves of the compute are replayed from per-slot CUDA graphs; the copies and the events that
+// order them are enqueued directly.
+constexpr int kHostSlots = RGNN_HOST_SLOTS;
+struct HostSlot {
+  cudaEvent_t pos_up, x0_up, graph_done, layers_done, done;
+  int32_t* flag_pinned;
+  uint64_t graph_key;
+  cudaGraphExec_t build_exec, layers_exec;
+  bool busy, has_work;
+};
+struct HostPipelineState {
+  cudaStream_t upload, compute, download;
+  cudaEvent_t start;
+  HostSlot slot[kHostSlots];
+  bool ok;
+};
+HostPipelineState* host_pipeline_state(bool create = true) {
+  static HostPipelineState per_device[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  HostPipelineState& h = per_device[dev];
+  if (!h.ok && !create) return nullptr;
+  if (!h.ok) {
+    if (cudaStreamCreateWithFlags(&h.upload, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h.compute, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h.download, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h.start, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    for (HostSlot& s : h.slot) {
+      cudaEvent_t* evs[] = {&s.pos_up, &s.x0_up, &s.graph_done, &s.layers_done, &s.done};
+      for (cudaEvent_t* e : evs)
+        if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      if (cudaMallocHost(reinterpret_cast<void**>(&s.flag_pinned), 64) != cudaSuccess) return nullptr;
+      s.graph_key = 0;
+      s.build_exec = s.layers_exec = nullptr;
+      s.busy = s.has_work = false;
+    }
+    h.ok = true;
+  }
+  return &h;
+}
+std::mutex& host_path_mutex() {
+  static std::mutex m;
+  return m;
+}
+
 inline void hash_bytes(uint64_t& h, const void* p, size_t n) {   // FNV-1a
   const unsigned char* b = static_cast<const unsigned char*>(p);
   for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
@@ -147,11 +196,15 @@ size_t rgnn_pipeline_workspace_bytes(const rgnn_pipeline_desc* desc, int64_t n_p
 }  // extern "C"
 
 // x0_ready (optional): event the stream waits for before the first layer reads x0; graph_done (optional):
-// recorded once edge_index / edge_attr are final -- the host entry point overlaps its copies with them
+// recorded once edge_index / edge_attr are final -- the host entry point overlaps its copies with them.
+// phases: kPhaseBuild (neighbour search .. CSC view) | kPhaseLayers (the conv stack); the pipelined host
+// entry point enqueues the two halves separately so that its copies can be ordered between them.
+enum { kPhaseBuild = 1, kPhaseLayers = 2, kPhaseAll = 3 };
 static int pipeline_forward_impl(const rgnn_pipeline_desc* desc, const float* pos, const float* vel, const float* x0,
                                  const int64_t* frame_ptr_host, int32_t n_frames, int64_t* edge_index, int64_t n_edges,
                                  float* edge_attr, float* h, int32_t* error_flag, void* workspace,
-                                 size_t workspace_bytes, cudaStream_t stream, cudaEvent_t x0_ready, cudaEvent_t graph_done) {
+                                 size_t workspace_bytes, cudaStream_t stream, cudaEvent_t x0_ready, cudaEvent_t graph_done,
+                                 int phases = kPhaseAll) {
   rgnn_stream_t stream_ = static_cast<rgnn_stream_t>(stream);
   int32_t de = 0, c_max = 0;
   RGNN_RETURN_IF_ERROR(validate(desc, &de, &c_max));
@@ -167,9 +220,10 @@ static int pipeline_forward_impl(const rgnn_pipeline_desc* desc, const float* po
   PipelineWorkspace w;
   RGNN_RETURN_IF_ERROR(carve(arena, desc, n, n_frames, n_edges, de, c_max, true, &w));
   if (arena.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
-  RGNN_CUDA_CHECK(cudaMemsetAsync(error_flag, 0, sizeof(int32_t), stream));
+  if (phases & kPhaseBuild) RGNN_CUDA_CHECK(cudaMemsetAsync(error_flag, 0, sizeof(int32_t), stream));
   if (n == 0) return RGNN_OK;
 
+  if (phases & kPhaseBuild) {
   // ---- 1. neighbour search -> edge_index ---------------------------------------------
   const float* basis = pos;
   if (desc->distance_dims == 4) {
@@ -226,9 +280,11 @@ static int pipeline_forward_impl(const rgnn_pipeline_desc* desc, const float* po
                                  stream, w.graph.rank));
   RGNN_RETURN_IF_ERROR(gather_edge_rows(edge_attr, w.csc_eid, n_edges, de, w.ea_csc, stream));
   }
+  }   // kPhaseBuild
 
   if (graph_done != nullptr) RGNN_CUDA_CHECK(cudaEventRecord(graph_done, stream));
   if (x0_ready != nullptr) RGNN_CUDA_CHECK(cudaStreamWaitEvent(stream, x0_ready, 0));
+  if (!(phases & kPhaseLayers)) return RGNN_OK;
 
   // ---- 4. conv -> BatchNorm(train) -> ReLU, L times ------------------------------------------
   ConvInput in;
@@ -295,75 +351,54 @@ size_t rgnn_pipeline_host_workspace_bytes(const rgnn_pipeline_desc* desc, int64_
   return a.used;
 }
 
-int rgnn_pipeline_forward_host(const rgnn_pipeline_desc* desc, const float* pos_host, const float* vel_host,
-                               const float* x0_host, int32_t c0, const int64_t* frame_ptr_host, int32_t n_frames,
-                               int64_t* edge_index_host, int64_t n_edges, float* edge_attr_host, float* h_host,
-                               void* workspace, size_t workspace_bytes, rgnn_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  int32_t de = 0, c_max = 0;
-  RGNN_RETURN_IF_ERROR(validate(desc, &de, &c_max));
+}  // extern "C"
+
+namespace {
+
+// Device staging area of one host-buffer call, carved from the caller's workspace.
+struct HostCall {
+  int32_t de, c_last;
+  int64_t n;
+  float *pos, *vel, *x0;
+  int64_t* edge_index;
+  float *edge_attr, *h;
+  int32_t* flag;
+  char* inner_ws;
+  size_t inner;
+};
+
+int carve_host_call(const rgnn_pipeline_desc* desc, const float* pos_host, const float* vel_host, const float* x0_host,
+                    int32_t c0, const int64_t* frame_ptr_host, int32_t n_frames, int64_t n_edges, void* workspace,
+                    size_t workspace_bytes, HostCall* c) {
+  int32_t c_max = 0;
+  RGNN_RETURN_IF_ERROR(validate(desc, &c->de, &c_max));
   if (frame_ptr_host == nullptr || n_frames < 1 || n_edges < 0 || c0 != desc->layers[0].in_channels) return RGNN_ERR_INVALID_ARGUMENT;
   const int64_t n = frame_ptr_host[n_frames];
   if (n < 0) return RGNN_ERR_INVALID_ARGUMENT;
   if (n > 0 && (pos_host == nullptr || vel_host == nullptr || x0_host == nullptr)) return RGNN_ERR_INVALID_ARGUMENT;
   const size_t need = rgnn_pipeline_host_workspace_bytes(desc, n, n_frames, n_edges, c0);
   if (workspace == nullptr || need == 0 || workspace_bytes < need) return RGNN_ERR_WORKSPACE_TOO_SMALL;
-  const int32_t c_last = desc->layers[desc->n_layers - 1].out_channels;
+  c->n = n;
+  c->c_last = desc->layers[desc->n_layers - 1].out_channels;
   Arena a(workspace, workspace_bytes);
-  float* pos = a.take<float>(static_cast<size_t>(n) * 2);
-  float* vel = a.take<float>(static_cast<size_t>(n) * 2);
-  float* x0 = a.take<float>(static_cast<size_t>(n) * c0);
-  int64_t* edge_index = a.take<int64_t>(static_cast<size_t>(n_edges) * 2);
-  float* edge_attr = a.take<float>(static_cast<size_t>(n_edges) * de);
-  float* h = a.take<float>(static_cast<size_t>(n) * c_last);
-  int32_t* flag = a.take<int32_t>(64);
-  const size_t inner = rgnn_pipeline_workspace_bytes(desc, n, n_frames, n_edges);
-  char* inner_ws = a.take<char>(inner);
-  if (a.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
-  // Copies overlap the compute: x0 (the bulk of the input) travels on a side stream while the main stream
-  // builds the graph, and edge_index / edge_attr travel back while the layers run.  The whole sequence
-  // (copies, ~40 kernels, cross-stream events) is captured into a CUDA graph the first time it is seen and
-  // replayed while the arguments stay the same: the eager launches cost ~0.1 ms of host time per call.
-  // one call at a time per process: the per-device streams, events and the cached graph are shared state
-  static std::mutex host_path_mutex;
-  std::lock_guard<std::mutex> host_path_lock(host_path_mutex);
-  HostPathStreams* hs = host_path_streams();
-  if (hs == nullptr) return RGNN_ERR_CUDA;
-  cudaStream_t ms = hs->main;
-  RGNN_CUDA_CHECK(cudaEventRecord(hs->start, stream));   // order our stream after the caller's
-  RGNN_CUDA_CHECK(cudaStreamWaitEvent(ms, hs->start, 0));
+  c->pos = a.take<float>(static_cast<size_t>(n) * 2);
+  c->vel = a.take<float>(static_cast<size_t>(n) * 2);
+  c->x0 = a.take<float>(static_cast<size_t>(n) * c0);
+  c->edge_index = a.take<int64_t>(static_cast<size_t>(n_edges) * 2);
+  c->edge_attr = a.take<float>(static_cast<size_t>(n_edges) * c->de);
+  c->h = a.take<float>(static_cast<size_t>(n) * c->c_last);
+  c->flag = a.take<int32_t>(64);
+  c->inner = rgnn_pipeline_workspace_bytes(desc, n, n_frames, n_edges);
+  c->inner_ws = a.take<char>(c->inner);
+  return a.overflow ? RGNN_ERR_WORKSPACE_TOO_SMALL : RGNN_OK;
+}
 
-  auto enqueue = [&]() -> int {
-    if (n > 0) {
-      RGNN_CUDA_CHECK(cudaMemcpyAsync(pos, pos_host, sizeof(float) * n * 2, cudaMemcpyHostToDevice, ms));
-      RGNN_CUDA_CHECK(cudaMemcpyAsync(vel, vel_host, sizeof(float) * n * 2, cudaMemcpyHostToDevice, ms));
-      RGNN_CUDA_CHECK(cudaEventRecord(hs->x0_ready, ms));                 // fork the side stream
-      RGNN_CUDA_CHECK(cudaStreamWaitEvent(hs->copy, hs->x0_ready, 0));
-      RGNN_CUDA_CHECK(cudaMemcpyAsync(x0, x0_host, sizeof(float) * n * c0, cudaMemcpyHostToDevice, hs->copy));
-      RGNN_CUDA_CHECK(cudaEventRecord(hs->x0_ready, hs->copy));
-    }
-    RGNN_RETURN_IF_ERROR(pipeline_forward_impl(desc, pos, vel, x0, frame_ptr_host, n_frames, edge_index, n_edges,
-                                               edge_attr, h, flag, inner_ws, inner, ms, n > 0 ? hs->x0_ready : nullptr,
-                                               n > 0 ? hs->graph_done : nullptr));
-    if (n > 0) {
-      RGNN_CUDA_CHECK(cudaStreamWaitEvent(hs->copy, hs->graph_done, 0));
-      if (edge_index_host != nullptr && n_edges > 0)
-        RGNN_CUDA_CHECK(cudaMemcpyAsync(edge_index_host, edge_index, sizeof(int64_t) * n_edges * 2, cudaMemcpyDeviceToHost, hs->copy));
-      if (edge_attr_host != nullptr && n_edges > 0 && de > 0)
-        RGNN_CUDA_CHECK(cudaMemcpyAsync(edge_attr_host, edge_attr, sizeof(float) * n_edges * de, cudaMemcpyDeviceToHost, hs->copy));
-      RGNN_CUDA_CHECK(cudaEventRecord(hs->copies_done, hs->copy));
-      RGNN_CUDA_CHECK(cudaStreamWaitEvent(ms, hs->copies_done, 0));        // join
-    }
-    if (h_host != nullptr && n > 0)
-      RGNN_CUDA_CHECK(cudaMemcpyAsync(h_host, h, sizeof(float) * n * c_last, cudaMemcpyDeviceToHost, ms));
-    RGNN_CUDA_CHECK(cudaMemcpyAsync(hs->flag_pinned, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ms));
-    return RGNN_OK;
-  };
-
-  // replay key: every argument the enqueued work depends on (pointers are compared, not their targets --
-  // buffers are read when the graph runs)
-  static int graph_enabled = -1;
-  if (graph_enabled < 0) { const char* e = getenv("RGNN_HOST_GRAPH"); graph_enabled = (e != nullptr && e[0] == '0') ? 0 : 1; }
+// replay key: every argument the enqueued work depends on (pointers are compared, not their targets --
+// buffers are read when the graph runs)
+uint64_t host_call_key(const rgnn_pipeline_desc* desc, const void* pos_host, const void* vel_host, const void* x0_host,
+                       int32_t c0, const int64_t* frame_ptr_host, int32_t n_frames, const void* edge_index_host,
+                       int64_t n_edges, const void* edge_attr_host, const void* h_host, const void* workspace,
+                       size_t workspace_bytes) {
   uint64_t key = 1469598103934665603ull;
   hash_bytes(key, desc, sizeof(*desc));
   hash_bytes(key, desc->layers, sizeof(rgnn_conv_desc) * desc->n_layers);
@@ -376,34 +411,200 @@ int rgnn_pipeline_forward_host(const rgnn_pipeline_desc* desc, const float* pos_
   hash_bytes(key, ptrs, sizeof(ptrs));
   const int64_t nums[] = {c0, n_frames, n_edges, static_cast<int64_t>(workspace_bytes)};
   hash_bytes(key, nums, sizeof(nums));
-  if (key == 0) key = 1;
+  return key == 0 ? 1 : key;
+}
 
-  bool launched = false;
-  if (graph_enabled && n > 0 && desc->search == 0) {
-    if (hs->graph_exec != nullptr && hs->graph_key == key) {
-      launched = cudaGraphLaunch(hs->graph_exec, ms) == cudaSuccess;
-    } else {
-      if (hs->graph_exec != nullptr) { cudaGraphExecDestroy(hs->graph_exec); hs->graph_exec = nullptr; hs->graph_key = 0; }
-      if (cudaStreamBeginCapture(ms, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        const int st = enqueue();
-        cudaGraph_t graph = nullptr;
-        const cudaError_t ce = cudaStreamEndCapture(ms, &graph);
-        if (st == RGNN_OK && ce == cudaSuccess && graph != nullptr &&
-            cudaGraphInstantiate(&hs->graph_exec, graph, 0) == cudaSuccess) {
-          hs->graph_key = key;
-          launched = cudaGraphLaunch(hs->graph_exec, ms) == cudaSuccess;
-        } else {
-          hs->graph_exec = nullptr;
-          (void)cudaGetLastError();   // a failed capture falls back to eager launches below
-        }
-        if (graph != nullptr) cudaGraphDestroy(graph);
-        if (st != RGNN_OK && st != RGNN_ERR_CUDA) return st;   // argument errors are the caller's
-      }
+bool host_graphs_enabled() {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("RGNN_HOST_GRAPH"); enabled = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return enabled != 0;
+}
+
+// Captures what `enqueue` puts on `stream` into *exec (replacing what it held).  Returns RGNN_OK with *exec == nullptr
+// when the capture itself failed (the caller then launches eagerly), the status of `enqueue` when that is the
+// caller's error.
+template <typename F>
+int capture_graph(cudaStream_t stream, F&& enqueue, cudaGraphExec_t* exec) {
+  if (*exec != nullptr) { cudaGraphExecDestroy(*exec); *exec = nullptr; }
+  if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { (void)cudaGetLastError(); return RGNN_OK; }
+  const int st = enqueue();
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+  if (!(st == RGNN_OK && ce == cudaSuccess && graph != nullptr && cudaGraphInstantiate(exec, graph, 0) == cudaSuccess)) {
+    *exec = nullptr;
+    (void)cudaGetLastError();
+  }
+  if (graph != nullptr) cudaGraphDestroy(graph);
+  return (st != RGNN_OK && st != RGNN_ERR_CUDA) ? st : RGNN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rgnn_pipeline_forward_host(const rgnn_pipeline_desc* desc, const float* pos_host, const float* vel_host,
+                               const float* x0_host, int32_t c0, const int64_t* frame_ptr_host, int32_t n_frames,
+                               int64_t* edge_index_host, int64_t n_edges, float* edge_attr_host, float* h_host,
+                               void* workspace, size_t workspace_bytes, rgnn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  HostCall c;
+  RGNN_RETURN_IF_ERROR(carve_host_call(desc, pos_host, vel_host, x0_host, c0, frame_ptr_host, n_frames, n_edges, workspace,
+                                       workspace_bytes, &c));
+  const int64_t n = c.n;
+  const int32_t de = c.de;
+  // Copies overlap the compute: x0 (the bulk of the input) travels on a side stream while the main stream
+  // builds the graph, and edge_index / edge_attr travel back while the layers run.  The whole sequence
+  // (copies, ~40 kernels, cross-stream events) is captured into a CUDA graph the first time it is seen and
+  // replayed while the arguments stay the same: the eager launches cost ~0.1 ms of host time per call.
+  // one call at a time per process: the per-device streams, events and the cached graph are shared state
+  std::lock_guard<std::mutex> host_path_lock(host_path_mutex());
+  HostPathStreams* hs = host_path_streams();
+  if (hs == nullptr) return RGNN_ERR_CUDA;
+  cudaStream_t ms = hs->main;
+  RGNN_CUDA_CHECK(cudaEventRecord(hs->start, stream));   // order our stream after the caller's
+  RGNN_CUDA_CHECK(cudaStreamWaitEvent(ms, hs->start, 0));
+  {
+    // ... and after the calls still in flight on the pipelined path (running statistics stay in call order)
+    HostPipelineState* ps = host_pipeline_state(false);
+    if (ps != nullptr) {
+      for (HostSlot& s : ps->slot)
+        if (s.busy && s.has_work) RGNN_CUDA_CHECK(cudaStreamWaitEvent(ms, s.done, 0));
     }
+  }
+
+  auto enqueue = [&]() -> int {
+    if (n > 0) {
+      RGNN_CUDA_CHECK(cudaMemcpyAsync(c.pos, pos_host, sizeof(float) * n * 2, cudaMemcpyHostToDevice, ms));
+      RGNN_CUDA_CHECK(cudaMemcpyAsync(c.vel, vel_host, sizeof(float) * n * 2, cudaMemcpyHostToDevice, ms));
+      RGNN_CUDA_CHECK(cudaEventRecord(hs->x0_ready, ms));                 // fork the side stream
+      RGNN_CUDA_CHECK(cudaStreamWaitEvent(hs->copy, hs->x0_ready, 0));
+      RGNN_CUDA_CHECK(cudaMemcpyAsync(c.x0, x0_host, sizeof(float) * n * c0, cudaMemcpyHostToDevice, hs->copy));
+      RGNN_CUDA_CHECK(cudaEventRecord(hs->x0_ready, hs->copy));
+    }
+    RGNN_RETURN_IF_ERROR(pipeline_forward_impl(desc, c.pos, c.vel, c.x0, frame_ptr_host, n_frames, c.edge_index, n_edges,
+                                               c.edge_attr, c.h, c.flag, c.inner_ws, c.inner, ms, n > 0 ? hs->x0_ready : nullptr,
+                                               n > 0 ? hs->graph_done : nullptr));
+    if (n > 0) {
+      RGNN_CUDA_CHECK(cudaStreamWaitEvent(hs->copy, hs->graph_done, 0));
+      if (edge_index_host != nullptr && n_edges > 0)
+        RGNN_CUDA_CHECK(cudaMemcpyAsync(edge_index_host, c.edge_index, sizeof(int64_t) * n_edges * 2, cudaMemcpyDeviceToHost, hs->copy));
+      if (edge_attr_host != nullptr && n_edges > 0 && de > 0)
+        RGNN_CUDA_CHECK(cudaMemcpyAsync(edge_attr_host, c.edge_attr, sizeof(float) * n_edges * de, cudaMemcpyDeviceToHost, hs->copy));
+      RGNN_CUDA_CHECK(cudaEventRecord(hs->copies_done, hs->copy));
+      RGNN_CUDA_CHECK(cudaStreamWaitEvent(ms, hs->copies_done, 0));        // join
+    }
+    if (h_host != nullptr && n > 0)
+      RGNN_CUDA_CHECK(cudaMemcpyAsync(h_host, c.h, sizeof(float) * n * c.c_last, cudaMemcpyDeviceToHost, ms));
+    RGNN_CUDA_CHECK(cudaMemcpyAsync(hs->flag_pinned, c.flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ms));
+    return RGNN_OK;
+  };
+
+  const uint64_t key = host_call_key(desc, pos_host, vel_host, x0_host, c0, frame_ptr_host, n_frames, edge_index_host, n_edges,
+                                     edge_attr_host, h_host, workspace, workspace_bytes);
+  bool launched = false;
+  if (host_graphs_enabled() && n > 0 && desc->search == 0) {
+    if (hs->graph_exec == nullptr || hs->graph_key != key) {
+      hs->graph_key = 0;
+      RGNN_RETURN_IF_ERROR(capture_graph(ms, enqueue, &hs->graph_exec));
+      if (hs->graph_exec != nullptr) hs->graph_key = key;
+    }
+    if (hs->graph_exec != nullptr) launched = cudaGraphLaunch(hs->graph_exec, ms) == cudaSuccess;
   }
   if (!launched) RGNN_RETURN_IF_ERROR(enqueue());
   RGNN_CUDA_CHECK(cudaStreamSynchronize(ms));
   const int32_t flag_host = *hs->flag_pinned;
+  return flag_host != 0 ? flag_host : RGNN_OK;
+}
+
+int rgnn_pipeline_submit_host(int32_t slot, const rgnn_pipeline_desc* desc, const float* pos_host, const float* vel_host,
+                              const float* x0_host, int32_t c0, const int64_t* frame_ptr_host, int32_t n_frames,
+                              int64_t* edge_index_host, int64_t n_edges, float* edge_attr_host, float* h_host,
+                              void* workspace, size_t workspace_bytes, rgnn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (slot < 0 || slot >= kHostSlots) return RGNN_ERR_INVALID_ARGUMENT;
+  HostCall c;
+  RGNN_RETURN_IF_ERROR(carve_host_call(desc, pos_host, vel_host, x0_host, c0, frame_ptr_host, n_frames, n_edges, workspace,
+                                       workspace_bytes, &c));
+  const int64_t n = c.n;
+  const int32_t de = c.de;
+  std::lock_guard<std::mutex> host_path_lock(host_path_mutex());
+  HostPipelineState* ps = host_pipeline_state();
+  if (ps == nullptr) return RGNN_ERR_CUDA;
+  HostSlot& s = ps->slot[slot];
+  if (s.busy) return RGNN_ERR_INVALID_ARGUMENT;   // rgnn_pipeline_wait_host(slot) first
+  *s.flag_pinned = 0;
+  if (n == 0) { s.busy = true; s.has_work = false; return RGNN_OK; }
+
+  auto build = [&]() -> int {
+    return pipeline_forward_impl(desc, c.pos, c.vel, c.x0, frame_ptr_host, n_frames, c.edge_index, n_edges, c.edge_attr, c.h,
+                                 c.flag, c.inner_ws, c.inner, ps->compute, nullptr, nullptr, kPhaseBuild);
+  };
+  auto layers = [&]() -> int {
+    return pipeline_forward_impl(desc, c.pos, c.vel, c.x0, frame_ptr_host, n_frames, c.edge_index, n_edges, c.edge_attr, c.h,
+                                 c.flag, c.inner_ws, c.inner, ps->compute, nullptr, nullptr, kPhaseLayers);
+  };
+  const bool use_graphs = host_graphs_enabled() && desc->search == 0;
+  if (use_graphs) {
+    const uint64_t key = host_call_key(desc, pos_host, vel_host, x0_host, c0, frame_ptr_host, n_frames, edge_index_host,
+                                       n_edges, edge_attr_host, h_host, workspace, workspace_bytes);
+    if (s.graph_key != key || s.build_exec == nullptr || s.layers_exec == nullptr) {
+      s.graph_key = 0;
+      RGNN_RETURN_IF_ERROR(capture_graph(ps->compute, build, &s.build_exec));
+      RGNN_RETURN_IF_ERROR(capture_graph(ps->compute, layers, &s.layers_exec));
+      if (s.build_exec != nullptr && s.layers_exec != nullptr) s.graph_key = key;
+    }
+  }
+  const bool replay = use_graphs && s.graph_key != 0;
+
+  // upload: positions first (the neighbour search needs only them), the node features behind
+  RGNN_CUDA_CHECK(cudaEventRecord(ps->start, stream));   // order the call after the caller's stream
+  RGNN_CUDA_CHECK(cudaStreamWaitEvent(ps->upload, ps->start, 0));
+  RGNN_CUDA_CHECK(cudaMemcpyAsync(c.pos, pos_host, sizeof(float) * n * 2, cudaMemcpyHostToDevice, ps->upload));
+  RGNN_CUDA_CHECK(cudaMemcpyAsync(c.vel, vel_host, sizeof(float) * n * 2, cudaMemcpyHostToDevice, ps->upload));
+  RGNN_CUDA_CHECK(cudaEventRecord(s.pos_up, ps->upload));
+  RGNN_CUDA_CHECK(cudaMemcpyAsync(c.x0, x0_host, sizeof(float) * n * c0, cudaMemcpyHostToDevice, ps->upload));
+  RGNN_CUDA_CHECK(cudaEventRecord(s.x0_up, ps->upload));
+  // compute: graph build, then the layers once the node features have arrived
+  RGNN_CUDA_CHECK(cudaStreamWaitEvent(ps->compute, s.pos_up, 0));
+  if (replay) RGNN_CUDA_CHECK(cudaGraphLaunch(s.build_exec, ps->compute));
+  else RGNN_RETURN_IF_ERROR(build());
+  RGNN_CUDA_CHECK(cudaEventRecord(s.graph_done, ps->compute));
+  RGNN_CUDA_CHECK(cudaStreamWaitEvent(ps->compute, s.x0_up, 0));
+  if (replay) RGNN_CUDA_CHECK(cudaGraphLaunch(s.layers_exec, ps->compute));
+  else RGNN_RETURN_IF_ERROR(layers());
+  RGNN_CUDA_CHECK(cudaEventRecord(s.layers_done, ps->compute));
+  // download: the graph while the layers run, the embeddings and the error flag behind them
+  RGNN_CUDA_CHECK(cudaStreamWaitEvent(ps->download, s.graph_done, 0));
+  if (edge_index_host != nullptr && n_edges > 0)
+    RGNN_CUDA_CHECK(cudaMemcpyAsync(edge_index_host, c.edge_index, sizeof(int64_t) * n_edges * 2, cudaMemcpyDeviceToHost, ps->download));
+  if (edge_attr_host != nullptr && n_edges > 0 && de > 0)
+    RGNN_CUDA_CHECK(cudaMemcpyAsync(edge_attr_host, c.edge_attr, sizeof(float) * n_edges * de, cudaMemcpyDeviceToHost, ps->download));
+  RGNN_CUDA_CHECK(cudaStreamWaitEvent(ps->download, s.layers_done, 0));
+  if (h_host != nullptr)
+    RGNN_CUDA_CHECK(cudaMemcpyAsync(h_host, c.h, sizeof(float) * n * c.c_last, cudaMemcpyDeviceToHost, ps->download));
+  RGNN_CUDA_CHECK(cudaMemcpyAsync(s.flag_pinned, c.flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ps->download));
+  RGNN_CUDA_CHECK(cudaEventRecord(s.done, ps->download));
+  s.busy = true;
+  s.has_work = true;
+  return RGNN_OK;
+}
+
+int rgnn_pipeline_wait_host(int32_t slot) {
+  if (slot < 0 || slot >= kHostSlots) return RGNN_ERR_INVALID_ARGUMENT;
+  cudaEvent_t done = nullptr;
+  HostSlot* s = nullptr;
+  {
+    std::lock_guard<std::mutex> host_path_lock(host_path_mutex());
+    HostPipelineState* ps = host_pipeline_state();
+    if (ps == nullptr) return RGNN_ERR_CUDA;
+    s = &ps->slot[slot];
+    if (!s->busy) return RGNN_ERR_INVALID_ARGUMENT;   // nothing submitted on this slot
+    if (s->has_work) done = s->done;
+  }
+  if (done != nullptr) RGNN_CUDA_CHECK(cudaEventSynchronize(done));   // outside the lock: other slots stay usable
+  std::lock_guard<std::mutex> host_path_lock(host_path_mutex());
+  const int32_t flag_host = *s->flag_pinned;
+  s->busy = s->has_work = false;
   return flag_host != 0 ? flag_host : RGNN_OK;
 }
 

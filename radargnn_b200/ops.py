@@ -16,7 +16,7 @@ from . import _lib
 __all__ = [
     "knn_graph", "radius_graph", "edge_features", "undirected_degree", "node_features", "csc_build",
     "CscGraph", "ConvParams", "conv_forward", "batchnorm_relu", "affine_relu", "sum_f32", "linear", "PipelineConfig",
-    "pipeline_forward", "pipeline_forward_host", "knn_edge_count",
+    "pipeline_forward", "pipeline_forward_host", "HostPipeline", "knn_edge_count",
 ]
 
 
@@ -509,6 +509,113 @@ def pipeline_forward_host(cfg: PipelineConfig, pos: np.ndarray, vel: np.ndarray,
             None if edge_attr is None else edge_attr.ctypes.data, h.ctypes.data, ws.data_ptr(), ws.numel(),
             _lib.stream_ptr()))
     return edge_index, edge_attr, h
+
+
+class HostPipeline:
+    """Batches through the host-buffer path with several calls in flight (rgnn_pipeline_submit_host /
+    rgnn_pipeline_wait_host): while batch i computes, batch i + 1 uploads and batch i - 1 downloads -- the role the
+    prefetching ``DataLoader`` plays in front of the reference's loop (gnn/trainer.py:210-233).
+
+        pipe = HostPipeline(cfg, depth=2)
+        for batch in batches:
+            if pipe.full:
+                edge_index, edge_attr, h = pipe.wait()      # oldest batch, numpy views of pinned memory
+            pipe.submit(batch.pos, batch.vel, batch.x0, batch.frame_ptr)
+        while pipe.in_flight:
+            edge_index, edge_attr, h = pipe.wait()
+
+    The arrays ``wait`` returns are views of the slot's pinned buffers: valid until ``depth`` further submits
+    (pass ``copy=True`` to own them).  k-NN graphs only: the edge count of a radius graph needs a device pass."""
+
+    def __init__(self, cfg: PipelineConfig, depth: int = 2, device="cuda:0", want_graph: bool = True):
+        _lib.require_device()
+        if not 1 <= depth <= _lib.HOST_SLOTS:
+            raise ValueError(f"depth must be in 1 .. {_lib.HOST_SLOTS}")
+        if cfg.algorithm != "knn":
+            raise ValueError("HostPipeline handles k-NN graphs (a radius graph's edge count needs a device pass)")
+        self.cfg, self.depth, self.want_graph = cfg, depth, want_graph
+        self.device = torch.device(device)
+        self._lib = _lib.load()
+        self._handle = _PipelineHandle(cfg)
+        self._slots = [{} for _ in range(depth)]
+        self._order: list = []      # slots in flight, oldest first
+        self._next = 0
+
+    @property
+    def in_flight(self) -> int:
+        return len(self._order)
+
+    @property
+    def full(self) -> bool:
+        return len(self._order) == self.depth
+
+    @staticmethod
+    def _pinned(slot: dict, name: str, shape, dtype) -> torch.Tensor:
+        """Pinned buffer of the slot, reallocated only when the batch outgrows it (the replay cache of the
+        library keys on the addresses)."""
+        need = int(np.prod(shape))
+        buf = slot.get(name)
+        if buf is None or buf.dtype != dtype or buf.numel() < need:
+            buf = torch.empty(max(need, 1), dtype=dtype).pin_memory()
+            slot[name] = buf
+        return buf[:need].view(*shape)
+
+    def submit(self, pos: np.ndarray, vel: np.ndarray, x0: np.ndarray, frame_ptr=None) -> None:
+        if self.full:
+            raise RuntimeError("every slot is in flight: wait() first")
+        lib, handle = self._lib, self._handle
+        n = int(pos.shape[0])
+        fp = _frame_ptr(frame_ptr, n)
+        n_edges = knn_edge_count(fp, self.cfg.k)
+        c0 = int(x0.shape[1])
+        idx = self._next
+        slot = self._slots[idx]
+        pos_p = self._pinned(slot, "pos", (n, 2), torch.float32)
+        vel_p = self._pinned(slot, "vel", (n, 2), torch.float32)
+        x0_p = self._pinned(slot, "x0", (n, c0), torch.float32)
+        pos_p.copy_(torch.from_numpy(np.ascontiguousarray(pos, dtype=np.float32)))
+        vel_p.copy_(torch.from_numpy(np.ascontiguousarray(vel, dtype=np.float32)))
+        x0_p.copy_(torch.from_numpy(np.ascontiguousarray(x0, dtype=np.float32)))
+        h = self._pinned(slot, "h", (n, self.cfg.layers[-1].out_channels), torch.float32)
+        ei = self._pinned(slot, "edge_index", (2, n_edges), torch.int64) if self.want_graph else None
+        ea = self._pinned(slot, "edge_attr", (n_edges, handle.edge_dim), torch.float32) if self.want_graph else None
+        with torch.cuda.device(self.device):
+            need = lib.rgnn_pipeline_host_workspace_bytes(C.byref(handle.desc), n, len(fp) - 1, n_edges, c0)
+            if need == 0:
+                raise ValueError("invalid pipeline configuration")
+            ws = slot.get("ws")
+            if ws is None or ws.numel() < need:
+                ws = slot["ws"] = _lib.workspace(need, self.device)
+            slot["fp"] = fp   # read by the call: keep it alive
+            _lib.check(lib.rgnn_pipeline_submit_host(
+                idx, C.byref(handle.desc), pos_p.data_ptr(), vel_p.data_ptr(), x0_p.data_ptr(), c0, fp.ctypes.data,
+                len(fp) - 1, None if ei is None else ei.data_ptr(), n_edges, None if ea is None else ea.data_ptr(),
+                h.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+        slot["out"] = (ei, ea, h)
+        self._order.append(idx)
+        self._next = (idx + 1) % self.depth
+
+    def wait(self, copy: bool = False):
+        """Outputs of the oldest batch in flight: (edge_index, edge_attr, h) as numpy arrays."""
+        if not self._order:
+            raise RuntimeError("nothing in flight")
+        idx = self._order.pop(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.rgnn_pipeline_wait_host(idx))
+        out = tuple(None if t is None else (t.numpy().copy() if copy else t.numpy()) for t in self._slots[idx]["out"])
+        return out
+
+    def drain(self) -> None:
+        while self._order:
+            idx = self._order.pop(0)
+            with torch.cuda.device(self.device):
+                self._lib.rgnn_pipeline_wait_host(idx)
+
+    def __del__(self):
+        try:
+            self.drain()
+        except Exception:
+            pass
 
 
 # ---------------------------------------------------------------------------------------------

@@ -41,7 +41,7 @@ def test_every_entry_point_cites_the_reference():
 
 
 def test_status_strings_match_reference_messages(lib):
-    assert lib.rgnn_abi_version() == 3
+    assert lib.rgnn_abi_version() == 4
     assert lib.rgnn_status_string(0) == b"ok"
     assert lib.rgnn_status_string(2) == b"Expected n_neighbors < n_samples_fit"   # sklearn's ValueError text
     assert lib.rgnn_status_string(5) == b"Error in dot product calculation"        # features.py:56

@@ -556,6 +556,69 @@ def test_host_entry_point_replays_its_graph(ops):
     torch.testing.assert_close(d, device_path(two), rtol=0, atol=0)
 
 
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_host_pipeline_matches_single_calls(ops, depth):
+    """rgnn_pipeline_submit_host / rgnn_pipeline_wait_host with several batches in flight: every batch gives the bytes
+    of a synchronous rgnn_pipeline_forward_host call, in submission order, slots and replayed graphs reused, batches
+    of changing size (re-capture) and an empty batch included."""
+    params = _stack_params(2, 64, 64, 2, "MPNNConv", seed=7)
+    cfg = _pipeline_cfg(ops, params, 2, "MPNNConv", "max", algorithm="knn", k=8, edge_features=["relative_position"])
+    sizes = [2500, 2500, 2500, 1800, 2500, 0, 700, 2500, 2500]
+    batches = []
+    for i, n in enumerate(sizes):
+        fr = synthetic.uniform_square(max(n, 1), seed=20 + i)
+        X, V = fr.X_cc[:n].astype(np.float32), fr.V_cc_compensated[:n].astype(np.float32)
+        ptr = np.array([0, n // 3, n], dtype=np.int64) if n > 30 else np.array([0, n], dtype=np.int64)
+        batches.append((X, V, synthetic.node_embeddings(max(n, 1), 64, seed=40 + i)[:n], ptr))
+    want = [ops.pipeline_forward_host(cfg, *b) for b in batches]
+    pipe = ops.HostPipeline(cfg, depth=depth)
+    got = []
+    for b in batches:
+        if pipe.full:
+            got.append(pipe.wait(copy=True))
+        pipe.submit(*b)
+    assert pipe.in_flight == min(depth, len(batches))
+    while pipe.in_flight:
+        got.append(pipe.wait(copy=True))
+    assert len(got) == len(want)
+    for (ei, ea, h), (ei0, ea0, h0) in zip(got, want):
+        np.testing.assert_array_equal(ei, ei0)
+        np.testing.assert_array_equal(ea, ea0)
+        np.testing.assert_array_equal(h, h0)
+
+
+def test_host_pipeline_slot_errors(ops):
+    """Slot bookkeeping of the C-ABI: waiting on an idle slot, submitting to a busy one, slots out of range and an
+    error raised by the data (non-finite coordinates) reported by the wait."""
+    import ctypes as C
+    from radargnn_b200 import _lib
+    lib = _lib.load()
+    assert lib.rgnn_pipeline_wait_host(0) == 1            # RGNN_ERR_INVALID_ARGUMENT: nothing submitted
+    assert lib.rgnn_pipeline_wait_host(-1) == 1 and lib.rgnn_pipeline_wait_host(_lib.HOST_SLOTS) == 1
+    params = _stack_params(1, 64, 64, 2, "MPNNConv", seed=8)
+    cfg = _pipeline_cfg(ops, params, 1, "MPNNConv", "max", algorithm="knn", k=4, edge_features=["relative_position"])
+    fr = synthetic.uniform_square(500, seed=3)
+    x0 = synthetic.node_embeddings(500, 64, seed=2)
+    pipe = ops.HostPipeline(cfg, depth=2)
+    pipe.submit(fr.X_cc, fr.V_cc_compensated, x0)
+    handle = ops._PipelineHandle(cfg)
+    ptr = np.array([0, 500], dtype=np.int64)
+    slot = pipe._slots[0]
+    busy = lib.rgnn_pipeline_submit_host(0, C.byref(handle.desc), slot["pos"].data_ptr(), slot["vel"].data_ptr(),
+                                         slot["x0"].data_ptr(), 64, ptr.ctypes.data, 1, None, 2000, None,
+                                         slot["h"].data_ptr(), slot["ws"].data_ptr(), slot["ws"].numel(), None)
+    assert busy == 1                                       # slot 0 has not been waited for
+    pipe.wait()
+    bad = fr.X_cc.copy()
+    bad[17, 0] = np.nan
+    pipe.submit(bad, fr.V_cc_compensated, x0)
+    with pytest.raises(ValueError):                        # sklearn check_array: "Input contains NaN"
+        pipe.wait()
+    pipe.submit(fr.X_cc, fr.V_cc_compensated, x0)          # the slot is usable again
+    _, _, h = pipe.wait()
+    assert np.isfinite(h).all()
+
+
 @pytest.mark.parametrize("aggr", ["max", "mean", "min"])
 def test_fused_layer_degenerate_sizes(ops, aggr):
     """Fused aggregate + update kernel (C = 64 MPNNConv) on degenerate graphs: a single node, no edges at all, fewer
