@@ -525,7 +525,7 @@ def main_gpu(args, wl):
                       "ea": torch.empty((n_edges, handle.edge_dim), dtype=torch.float32).pin_memory(),
                       "ws": _lib.workspace(host_ws.numel(), dev)})
 
-    def run_pipelined(steps: int) -> float:
+    def run_pipelined(steps: int, full: bool = True) -> float:
         """Device-clock time of `steps` batches through submit / wait, every batch's copies and the drain included."""
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -537,7 +537,8 @@ def main_gpu(args, wl):
             flush.zero_()
             _lib.check(lib.rgnn_pipeline_submit_host(
                 i % depth, C.byref(handle.desc), pos_h.data_ptr(), vel_h.data_ptr(), x0_h.data_ptr(), wl["c0"],
-                ptr.ctypes.data, n_frames, sl["ei"].data_ptr(), n_edges, sl["ea"].data_ptr(), sl["h"].data_ptr(),
+                ptr.ctypes.data, n_frames, sl["ei"].data_ptr() if full else None, n_edges,
+                sl["ea"].data_ptr() if full else None, sl["h"].data_ptr(),
                 sl["ws"].data_ptr(), sl["ws"].numel(), sp))
             if world > 1:
                 all_reduce_loss()
@@ -575,6 +576,13 @@ def main_gpu(args, wl):
                       api="rgnn_pipeline_submit_host / rgnn_pipeline_wait_host (pinned host buffers), "
                           f"{depth} batches in flight, L2 flush inside the timed region",
                       batches_in_flight=depth, sync_call_ms_per_step=e2e["e2e_sync"]["ms_per_step"])
+    run_pipelined(4, full=False)
+    barrier()
+    t = max_over_ranks(run_pipelined(e2e_steps, full=False))
+    barrier()
+    e2e["e2e_embeddings_only"] = dict(e2e["e2e_embeddings_only"], value=n_edges * world * e2e_steps / t,
+                                      ms_per_step=t / e2e_steps * 1e3, api=e2e["e2e"]["api"], batches_in_flight=depth,
+                                      sync_call_ms_per_step=e2e["e2e_embeddings_only"]["ms_per_step"])
 
     # ---- roofline of the dominant kernel: per-kernel CUDA events over the same steps ----------------
     _lib.profile_reset()
