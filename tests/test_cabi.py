@@ -107,6 +107,9 @@ def test_compute_entry_points_fail_loudly_without_a_device(lib):
     from radargnn_b200.graph_constructor.graph import Graph
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Graph().build(np.zeros((3, 2)), "knn", k=1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.HostPipeline(None)
+    assert lib.rgnn_pipeline_wait_host(0) != 0 and lib.rgnn_pipeline_wait_host(99) == 1   # no device / slot out of range
 
 
 def test_product_never_imports_the_oracle():
