@@ -42,6 +42,8 @@ class Graph():
     # -- edge list: assigning E by hand drops the device copy and the cached adjacency matrix -----
     @property
     def E(self):
+        if self._E is None and self._edge_index_dev is not None and self._dev_in_E_order:
+            self._E = self._edge_index_dev.t().contiguous().cpu().numpy()   # adopted device edges: copied on first use
         return self._E
 
     @E.setter
@@ -80,6 +82,17 @@ class Graph():
         self._edge_index_dev = edge_index   # after the setter (which drops any stale device copy)
         self._dev_in_E_order = True
 
+    def adopt_edges(self, n_nodes: int, edge_index: Optional[torch.Tensor], E: Optional[np.ndarray] = None) -> None:
+        """Takes over an edge list built elsewhere (the batched constructor): a device ``edge_index`` [2, E] whose
+        rows are grouped by query point, or a host ``E`` [E, 2]."""
+        self._n = int(n_nodes)
+        if edge_index is not None:
+            self.E = None                      # the host copy is made when somebody reads E
+            self._edge_index_dev = edge_index
+            self._dev_in_E_order = True
+        else:
+            self.E = np.ascontiguousarray(E, dtype=np.int64)
+
     def __build_knn(self, X: np.ndarray, k: int) -> None:
         basis = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64), device=_device())
         self.__set_edges(X, ops.knn_graph(basis, k))
@@ -111,18 +124,26 @@ class Graph():
             self._n = max(self._n, int(E.max()) + 1 if E.size else 0)
         return self._edge_index_dev
 
-    def get_degree(self) -> list:
-        """Degree of every node of the undirected graph over ``A`` (reference graph.py:93-96)."""
-        if self.E is None:
+    def _ensure_edges(self) -> None:
+        """Adopts the edges of a hand-assigned adjacency matrix when no edge list exists."""
+        if self._E is None and self._edge_index_dev is None:
             A = self._A
             if A is None:
                 raise AttributeError("graph has not been built")
             rows, cols = np.nonzero(A)
             self.E = np.stack([rows, cols], axis=1).astype(np.int64)
+            self._A = A       # the E setter dropped it
             self._n = A.shape[0]
+
+    def get_degree(self) -> list:
+        """Degree of every node of the undirected graph over ``A`` (reference graph.py:93-96)."""
+        return self._degree_array().tolist()
+
+    def _degree_array(self) -> np.ndarray:
+        """``get_degree`` as an int64 array (no Python list in between)."""
+        self._ensure_edges()
         n = self._n if self._A is None else self._A.shape[0]
-        deg = ops.undirected_degree(self._edge_index(), n)
-        return [int(v) for v in deg.cpu().tolist()]
+        return ops.undirected_degree(self._edge_index(), n).cpu().numpy().astype(np.int64, copy=False)
 
     def show(self, node_size: float = 60) -> None:  # pragma: no cover - plotting only
         import matplotlib.pyplot as plt
@@ -149,9 +170,8 @@ class GeometricGraph(Graph):
             self.F[name] = F_add
 
     def add_degree_to_inv_features(self) -> None:
-        deg = self.get_degree()
-        deg_arr = np.array([deg]).reshape(len(deg), 1)
-        self.add_invariant_feature("degree", deg_arr)
+        deg = self._degree_array()
+        self.add_invariant_feature("degree", deg.reshape(len(deg), 1))
 
     def extract_node_pair_features(self, features: List[str], edge_mode: str) -> None:
         """Edge feature matrix ``E_feat`` [E, De] (fp64), columns in list order
@@ -164,9 +184,11 @@ class GeometricGraph(Graph):
         else:
             ei = torch.as_tensor(np.ascontiguousarray(np.asarray(self.E, dtype=np.int64).T), device=dev)
         feat = ops.edge_features(pos, vel, ei, features, edge_mode, out_dtype=torch.float64)
+        feat = feat.cpu().numpy()
         if self.E_feat is None:
-            self.E_feat = np.empty([self.E.shape[0], feat.shape[1]])
-        self.E_feat[:, :] = feat.cpu().numpy()
+            self.E_feat = feat
+        else:
+            self.E_feat[:, :] = feat
 
     def extract_single_node_features(self, features: List[str]) -> None:
         """Node feature matrix ``X_feat`` [N, Fn], columns in list order (reference graph.py:225-275)."""

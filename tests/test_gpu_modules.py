@@ -145,6 +145,47 @@ def test_build_geometric_graph_matches_reference_golden(name):
     assert tuple(data.edge_index.shape) == (2, fx["E"].shape[0]) and data.edge_attr.dtype == torch.float32
 
 
+@pytest.mark.parametrize("algo,dd,node_features,edge_features,edge_mode", [
+    ("knn", "X", ["rcs", "spatial_coordinates"], ["relative_position"], "directed"),
+    ("knn", "XV", ["rcs", "time_index", "degree", "velocity_vector_length", "velocity_vector"],
+     ["point_pair_features", "relative_velocity"], "directed"),
+    ("radius", "X", ["time_index", "degree"], ["spatial_euclidean_distance", "point_pair_features"], "undirected"),
+])
+def test_build_geometric_graphs_equals_per_frame_calls(algo, dd, node_features, edge_features, edge_mode):
+    """Batched boundary function (all frames of a list in one device pass, the loop of dataset_creation.py:651-660):
+    every graph equals the one ``build_geometric_graph`` builds for that frame alone, bit for bit."""
+    from radargnn_b200 import synthetic
+    from radargnn_b200.preprocessor import GraphConstructionConfiguration, GraphConstructor, RadarPointCloud
+    clouds = []
+    for s, n in enumerate([300, 7, 120, 2, 451]):
+        fr = synthetic.radar_frame(n, seed=60 + s)
+        pc = RadarPointCloud()
+        pc.X_cc, pc.V_cc_compensated = fr.X_cc, fr.V_cc_compensated
+        rng = np.random.default_rng(s)
+        pc.rcs = rng.normal(size=(n, 1))
+        pc.timestamp = rng.integers(0, 4, size=(n, 1)).astype(np.float64) * 1.7e4 + 1.6e15
+        clouds.append(pc)
+    config = GraphConstructionConfiguration(algo, {"k": 1 if algo == "knn" else 6, "r": 4.0}, node_features, edge_features,
+                                            edge_mode, dd)
+    got = GraphConstructor.build_geometric_graphs(config, clouds)
+    assert len(got) == len(clouds)
+    for g, pc in zip(got, clouds):
+        want = GraphConstructor.build_geometric_graph(config, pc)
+        np.testing.assert_array_equal(g.E, want.E)
+        np.testing.assert_array_equal(g.E_feat, want.E_feat)
+        np.testing.assert_array_equal(g.X_feat, want.X_feat)
+        np.testing.assert_array_equal(g.A, want.A)
+        assert list(g.F) == list(want.F)
+        for name in g.F:
+            np.testing.assert_array_equal(g.F[name], want.F[name])
+        assert g.get_degree() == want.get_degree()
+    # a frame the single-frame function rejects (k >= n) is rejected by the batch as well
+    big_k = GraphConstructionConfiguration("knn", {"k": 7, "r": 1}, node_features, edge_features, edge_mode, dd)
+    with pytest.raises(ValueError):
+        GraphConstructor.build_geometric_graphs(big_k, clouds)
+    assert GraphConstructor.build_geometric_graphs(config, []) == []
+
+
 # ---- reference test/test_gnn.py ------------------------------------------------------------------------
 def _ones(seq):
     for layer in seq:
