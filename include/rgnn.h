@@ -299,9 +299,11 @@ int rgnn_nearest_neighbor(const void* basis, int32_t basis_dtype, int32_t dims, 
 
 /* time_index node feature (dataset_creation.py:214-223): position of the point's timestamp among the sorted
  * distinct timestamps of its frame, as double.  frame_ptr (device) and frame_ptr_host hold the same
- * [n_frames + 1] offsets; a frame may hold at most 8192 points. */
+ * [n_frames + 1] offsets.  Frames of up to 8192 points are ranked in shared memory (workspace may be NULL);
+ * a batch with a longer frame takes the global-memory path and needs rgnn_time_index_workspace_bytes(N). */
+size_t rgnn_time_index_workspace_bytes(int64_t n_points);
 int rgnn_time_index(const double* timestamp, const int64_t* frame_ptr, const int64_t* frame_ptr_host, int32_t n_frames,
-                    double* time_index, rgnn_stream_t stream);
+                    double* time_index, void* workspace, size_t workspace_bytes, rgnn_stream_t stream);
 
 /* Node-id offsets of the disjoint-union collate (utils/data_handling.py:30, PyG Batch.from_data_list):
  * edge_index [2, E] holds frame-local ids, columns edge_ptr[f] .. edge_ptr[f+1] belong to frame f (device

@@ -128,7 +128,9 @@ _PROTOTYPES = {
     "rgnn_nearest_neighbor_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "rgnn_nearest_neighbor": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_size_t, C.c_void_p]),
-    "rgnn_time_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "rgnn_time_index_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "rgnn_time_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t,
+                                  C.c_void_p]),
     "rgnn_collate_offsets": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
                                        C.c_void_p]),
     "rgnn_conv_backward_route": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,

@@ -313,6 +313,66 @@ time_index_kernel(const double* __restrict__ ts, const int64_t* __restrict__ fra
   }
 }
 
+// Frames above kTimeMax points: the same three steps in global memory.  The sort is the all-ascending bitonic
+// network (per merge of size k a mirror stage l = i ^ (k - 1), then l = i ^ j for j = k/4 .. 1): every comparator
+// orders its pair ascending, so the virtual +inf padding of a frame that is no power of two never moves and
+// comparators that reach past the frame's end are skipped; one launch per stage over all points of the batch.
+__device__ __forceinline__ int frame_of(const int64_t* __restrict__ frame_ptr, int n_frames, int64_t i) {
+  int lo = 0, hi = n_frames - 1;   // last f with frame_ptr[f] <= i
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (frame_ptr[mid] <= i) lo = mid; else hi = mid - 1; }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256)
+time_sort_stage_kernel(double* __restrict__ v, const int64_t* __restrict__ frame_ptr, int n_frames, int64_t n, int64_t k, int64_t j) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int f = frame_of(frame_ptr, n_frames, i);
+  const int64_t beg = frame_ptr[f], m = frame_ptr[f + 1] - beg, li = i - beg;
+  const int64_t l = j == 0 ? (li ^ (k - 1)) : (li ^ j);   // j == 0: the mirror stage of the merge of size k
+  if (l > li && l < m) {
+    const double a = v[beg + li], b = v[beg + l];
+    if (a > b) { v[beg + li] = b; v[beg + l] = a; }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+time_new_value_kernel(const double* __restrict__ v, const int64_t* __restrict__ frame_ptr, int n_frames, int64_t n, int32_t* __restrict__ flag) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t beg = frame_ptr[frame_of(frame_ptr, n_frames, i)];
+  flag[i] = (i > beg && v[i] != v[i - 1]) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+time_rank_kernel(const double* __restrict__ ts, const double* __restrict__ v, const int32_t* __restrict__ prefix,
+                 const int64_t* __restrict__ frame_ptr, int n_frames, int64_t n, double* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int f = frame_of(frame_ptr, n_frames, i);
+  const int64_t beg = frame_ptr[f], end = frame_ptr[f + 1];
+  const double t = ts[i];
+  int64_t lo = beg, hi = end - 1;   // first sorted position holding t
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (v[mid] < t) lo = mid + 1; else hi = mid; }
+  out[i] = static_cast<double>(prefix[lo + 1] - prefix[beg]);   // distinct values before it (flag[beg] = 0)
+}
+
+struct TimeIndexWorkspace {
+  double* sorted;      // [n]
+  int32_t* flag;       // [n]
+  int32_t* prefix;     // [n + 1]
+  int32_t* scan;       // scan_scratch_ints(n)
+};
+template <typename ArenaT>
+TimeIndexWorkspace carve_time_index(ArenaT& a, int64_t n) {
+  TimeIndexWorkspace w;
+  w.sorted = a.template take<double>(n);
+  w.flag = a.template take<int32_t>(n);
+  w.prefix = a.template take<int32_t>(n + 1);
+  w.scan = a.template take<int32_t>(scan_scratch_ints(n));
+  return w;
+}
+
 // ---- disjoint-union collate -----------------------------------------------------------------------------------
 // edge_index [2, E] holds frame-local node ids, the edges of frame f are columns edge_ptr[f] .. edge_ptr[f+1]:
 // add the frame's node offset to both rows (what PyG's Batch.from_data_list does to edge_index)
@@ -440,8 +500,15 @@ int rgnn_nearest_neighbor(const void* basis, int32_t basis_dtype, int32_t dims, 
   return RGNN_OK;
 }
 
+size_t rgnn_time_index_workspace_bytes(int64_t n_points) {
+  if (n_points < 0 || n_points > 0x7ffffff0LL) return 0;
+  SizeArena a;
+  carve_time_index(a, n_points);
+  return a.used;
+}
+
 int rgnn_time_index(const double* timestamp, const int64_t* frame_ptr, const int64_t* frame_ptr_host, int32_t n_frames,
-                    double* time_index, rgnn_stream_t stream_) {
+                    double* time_index, void* workspace, size_t workspace_bytes, rgnn_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (frame_ptr == nullptr || frame_ptr_host == nullptr || n_frames < 1) return RGNN_ERR_INVALID_ARGUMENT;
   int64_t longest = 0;
@@ -452,7 +519,28 @@ int rgnn_time_index(const double* timestamp, const int64_t* frame_ptr, const int
   }
   if (longest == 0) return RGNN_OK;
   if (timestamp == nullptr || time_index == nullptr) return RGNN_ERR_INVALID_ARGUMENT;
-  if (longest > kTimeMax) return RGNN_ERR_UNSUPPORTED;   // a frame's timestamps are sorted in shared memory
+  if (longest > kTimeMax) {
+    // a frame too long for the shared-memory sort: the global-memory path over the whole batch
+    const int64_t n = frame_ptr_host[n_frames];
+    if (n > 0x7ffffff0LL) return RGNN_ERR_INVALID_ARGUMENT;
+    if (workspace == nullptr || workspace_bytes < rgnn_time_index_workspace_bytes(n)) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+    Arena arena(workspace, workspace_bytes);
+    TimeIndexWorkspace w = carve_time_index(arena, n);
+    if (arena.overflow) return RGNN_ERR_WORKSPACE_TOO_SMALL;
+    RGNN_PROFILE("time_index", stream);
+    RGNN_CUDA_CHECK(cudaMemcpyAsync(w.sorted, timestamp, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+    const unsigned blocks = div_up(n, 256);
+    for (int64_t k = 2; (k >> 1) < longest; k <<= 1) {
+      time_sort_stage_kernel<<<blocks, 256, 0, stream>>>(w.sorted, frame_ptr, n_frames, n, k, 0);
+      for (int64_t j = k >> 2; j > 0; j >>= 1) time_sort_stage_kernel<<<blocks, 256, 0, stream>>>(w.sorted, frame_ptr, n_frames, n, k, j);
+    }
+    time_new_value_kernel<<<blocks, 256, 0, stream>>>(w.sorted, frame_ptr, n_frames, n, w.flag);
+    RGNN_LAUNCH_CHECK();
+    RGNN_RETURN_IF_ERROR(exclusive_scan_i32(w.flag, w.prefix, n, w.scan, stream));
+    time_rank_kernel<<<blocks, 256, 0, stream>>>(timestamp, w.sorted, w.prefix, frame_ptr, n_frames, n, time_index);
+    RGNN_LAUNCH_CHECK();
+    return RGNN_OK;
+  }
   int m2 = 1;
   while (m2 < longest) m2 <<= 1;
   const size_t smem = static_cast<size_t>(m2) * (sizeof(double) + sizeof(int));

@@ -704,7 +704,10 @@ def time_index(timestamp: torch.Tensor, frame_ptr=None) -> torch.Tensor:
     fp_dev = torch.from_numpy(fp).to(ts.device)
     out = torch.zeros(n, dtype=torch.float64, device=ts.device)
     with torch.cuda.device(ts.device):
+        # frames above 8192 points are ranked in global memory and need scratch
+        ws = _lib.workspace(lib.rgnn_time_index_workspace_bytes(n), ts.device) if int(np.diff(fp).max(initial=0)) > 8192 else None
         _lib.check(lib.rgnn_time_index(ts.data_ptr(), fp_dev.data_ptr(), fp.ctypes.data, len(fp) - 1, out.data_ptr(),
+                                       None if ws is None else ws.data_ptr(), 0 if ws is None else ws.numel(),
                                        _lib.stream_ptr()))
     return out
 

@@ -127,6 +127,28 @@ def test_time_index_matches_reference_loop(ops):
     np.testing.assert_array_equal(got, want)
 
 
+def test_time_index_large_frames(ops):
+    """Frames above 8192 points (the BASELINE frames of 10 k / 100 k / 125 k points) take the global-memory path:
+    few distinct stamps (radar sweeps), all-distinct stamps, sizes that are no power of two, short frames and an
+    empty frame in the same batch."""
+    rng = np.random.default_rng(3)
+    sizes = [10_000, 0, 300, 100_000, 8193, 1, 20_011]
+    ts = []
+    for f, m in enumerate(sizes):
+        if f == 4:
+            ts.append(rng.permutation(m).astype(np.float64) * 0.25)                       # every stamp distinct
+        elif f == 6:
+            ts.append(np.floor(rng.uniform(0, 5000, size=m)))                              # thousands of ties
+        else:
+            ts.append(rng.choice(np.array([0.0, 0.05, 0.1, 0.15, 17.5, 1.6e15]) + f, size=m))
+    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    got = ops.time_index(torch.from_numpy(np.concatenate(ts)).to(DEV), ptr).cpu().numpy()
+    want = np.concatenate([np.unique(t, return_inverse=True)[1].astype(np.float64) if t.size else t for t in ts])
+    np.testing.assert_array_equal(got, want)
+    small = do.time_index(ts[2])                                                           # the reference loop agrees
+    np.testing.assert_array_equal(got[ptr[2]:ptr[3]], small)
+
+
 def test_collate_offsets_match_disjoint_union(ops):
     g = torch.Generator().manual_seed(2)
     nodes, edges = [5, 0, 7, 3], [9, 0, 20, 2]
