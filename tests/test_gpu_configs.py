@@ -125,6 +125,33 @@ def test_config5_one_rank_125k(ops):
     _assert_embeddings(h, want)
 
 
+def test_headline_frame_through_the_boundary_function():
+    """The boundary function itself (GraphConstructor.build_geometric_graph, dataset_creation.py:187-229) on one
+    frame of the headline size: 100 k points, k = 16, node features [rcs, velocity_vector_length, time_index,
+    degree], relative_position.  Edges bit-exact against sklearn, features against vectorised numpy."""
+    import scipy.sparse as sp
+    from radargnn_b200.preprocessor import GraphConstructionConfiguration, GraphConstructor, RadarPointCloud
+    n, k = 100_000, 16
+    fr = synthetic.uniform_square(n, seed=0)
+    rng = np.random.default_rng(0)
+    pc = RadarPointCloud()
+    pc.X_cc, pc.V_cc_compensated = fr.X_cc, fr.V_cc_compensated
+    pc.rcs = rng.normal(size=(n, 1))
+    pc.timestamp = rng.integers(0, 7, size=(n, 1)).astype(np.float64) * 1.7e4 + 1.6e15
+    cfg = GraphConstructionConfiguration("knn", {"k": k, "r": 1.0}, ["rcs", "velocity_vector_length", "time_index", "degree"],
+                                         ["relative_position"], "directed", "X")
+    g = GraphConstructor.build_geometric_graph(cfg, pc)
+    E = go.knn_edges_sklearn(fr.X_cc, k)
+    np.testing.assert_array_equal(g.E, E)
+    np.testing.assert_array_equal(g.E_feat, fr.X_cc[E[:, 0]] - fr.X_cc[E[:, 1]])
+    A = sp.coo_matrix((np.ones(len(E)), (E[:, 0], E[:, 1])), shape=(n, n)).tocsr()
+    degree = np.asarray(((A + A.T) > 0).sum(axis=1)).reshape(-1)
+    t_idx = np.unique(pc.timestamp.reshape(-1), return_inverse=True)[1]
+    want = np.stack([pc.rcs[:, 0], np.linalg.norm(fr.V_cc_compensated, axis=1), t_idx.astype(np.float64),
+                     degree.astype(np.float64)], axis=1)
+    np.testing.assert_allclose(g.X_feat, want, rtol=1e-14, atol=0)
+
+
 def test_headline_100k_against_fp64_truth(ops):
     """The headline shape against the fp64 oracle (not the fp32 restatement), both metrics."""
     fr = synthetic.uniform_square(100_000, seed=0)
